@@ -1,0 +1,76 @@
+/*
+ * mrt_host.h — host-side scene API above the C-ABI boundary (libmrt_host.so, plain C++17, no CUDA).
+ *
+ * This is the part the north star leaves with the Rust host: the reference's scene API (World::new/add/
+ * build_bvh world.rs:101-122, Sphere::new geom.rs:46, Triangle::new :449, Model::new :281, Model::instance :312,
+ * Instance::with_material :392, Volume::new :603, Camera::new world.rs:16, PlyLoader::load ply_loader.rs:273,
+ * the materials of material.rs and surfaces of texture.rs) plus the `flatten()` walk that turns World.objects into
+ * the plain arrays of mrt_scene_desc. No Rust toolchain exists in this image, so the mirror is written in C++
+ * with a C surface; names, argument order and error behaviour follow the reference. Handles are small integers
+ * owned by the mrth_scene. Functions returning int give a handle >= 0 or a negative error (mrth_last_error).
+ */
+#ifndef MRT_HOST_H
+#define MRT_HOST_H
+#include "mrt.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrth_scene mrth_scene;
+
+mrth_scene* mrth_scene_new(void);
+void mrth_scene_free(mrth_scene*);
+const char* mrth_last_error(mrth_scene*);
+void mrth_seed(mrth_scene*, uint64_t seed); /* fastrand::seed main.rs:86 — drives BVH split axes (geom.rs:111) */
+float mrth_rand_f32(mrth_scene*);           /* f32::rand() math.rs:244 for scene generation */
+
+/* texture.rs */
+int mrth_surface_solid(mrth_scene*, float r, float g, float b, float a);
+int mrth_surface_texture(mrth_scene*, const uint8_t* rgba, uint32_t w, uint32_t h, int wrap); /* Texture::load_bytes :70 */
+int mrth_surface_ycbcr(mrth_scene*, int luma_tex, int chroma_tex);
+int mrth_surface_blend(mrth_scene*, int mode, int left, int right);
+int mrth_surface_fallback(mrth_scene*, float r, float g, float b, float a, int inner);
+
+/* material.rs */
+int mrth_mat_absorb(mrth_scene*);
+int mrth_mat_lambertian(mrth_scene*, int surface);
+int mrth_mat_diffuse_light(mrth_scene*, float r, float g, float b);
+int mrth_mat_metal(mrth_scene*, float fuzz, int surface);
+int mrth_mat_dielectric(mrth_scene*, float ior);
+int mrth_mat_specular(mrth_scene*, float ior, int surface);
+int mrth_mat_mix(mrth_scene*, float ratio, int left, int right);
+int mrth_mat_isotropic(mrth_scene*, float r, float g, float b);
+
+void mrth_background_solid(mrth_scene*, float r, float g, float b);
+void mrth_background_sky(mrth_scene*);
+void mrth_background_skysphere(mrth_scene*, int surface);
+void mrth_background_cubemap(mrth_scene*, const int surfaces6[6], float rx, float ry, float rz);
+
+/* geom.rs — a mesh is the Arc<BvhNode> of a Model; the BLAS is built at creation like Model::new */
+int mrth_mesh_new(mrth_scene*, const float* verts, uint64_t n_tris, int tri_material);
+int mrth_mesh_new_uv(mrth_scene*, const float* verts, const float* normals, const float* uvs, uint64_t n_tris, int tri_material);
+int mrth_mesh_load_ply(mrth_scene*, const char* path, const int perm[3], int tri_material, float* max_abs);
+uint64_t mrth_mesh_tri_count(mrth_scene*, int mesh);
+void mrth_mesh_get_verts(mrth_scene*, int mesh, float* out9);
+uint64_t mrth_mesh_node_count(mrth_scene*, int mesh);
+
+int mrth_add_sphere(mrth_scene*, int material, float cx, float cy, float cz, float radius);
+int mrth_add_model(mrth_scene*, int mesh, int override_material);
+int mrth_add_instance(mrth_scene*, int mesh, const float t[3], const float r[3], const float s[3], int override_material);
+int mrth_add_volume_sphere(mrth_scene*, float cx, float cy, float cz, float radius, float density, float r, float g, float b);
+void mrth_build_bvh(mrth_scene*);
+uint64_t mrth_tlas_node_count(mrth_scene*);
+void mrth_camera(mrth_scene*, float vfov, const float from[3], const float at[3], const float up[3], float aspect, float aperture, float focus);
+
+void mrth_get_camera(mrth_scene*, float out19[19]);
+void mrth_get_instance(mrth_scene*, int object, float transform16[16], float inv16[16], float aabb6[6]);
+void mrth_get_object_aabb(mrth_scene*, int object, float aabb6[6]);
+
+/* the flatten() walk: valid until the scene is mutated or freed */
+const mrt_scene_desc* mrth_scene_desc(mrth_scene*);
+const mrt_camera* mrth_scene_camera(mrth_scene*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1042 @@
+// mrt_cuda.cu — wavefront path tracer for sm_100a behind the C ABI of include/mrt.h.
+//
+// Replaces render() (reference src/main.rs:150-295). One context drives one GPU:
+//
+//   advance  (1 thread)      queue bookkeeping, hands out the next block of pixel samples
+//   generate (persistent)    Camera::ray for regenerated path slots               world.rs:53-63, main.rs:258-260
+//   extend   (persistent)    closest hit through TLAS/BLAS, classify by material   world.rs:68, geom.rs
+//   shade    (persistent)    emit + scatter per material-sorted queue, accumulate  world.rs:69-77, material.rs
+//
+// Path state lives in a fixed pool of slots (SoA, 64 B per slot). A slot whose path ends is refilled with the next
+// pixel sample in the same iteration ("regeneration"), so every extend launch works on a full pool until the job
+// drains. Queues hold slot indices; appends use one atomic per warp (ballot / match + popc + shuffle).
+// Radiance is accumulated as 64-bit fixed point (2^-32 units) with integer atomics: sums are exact and therefore
+// independent of sample order, of how a sample range is split over calls, and of the number of GPUs.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mrt.h"
+#include "mrt_debug.h"
+#include "mrt_device.cuh"
+
+namespace mrt {
+
+enum { Q_MISS = 0, Q_FIRST_MAT = 1, Q_COUNT = 1 + MRT_MAT_KINDS };
+
+struct QueueState {
+    uint32_t n_ext;        // rays traced this iteration = n_cont + n_new
+    uint32_t n_cont;       // continuing paths (written by the previous shade into the current extend queue)
+    uint32_t n_new;        // camera rays generated this iteration
+    uint32_t n_next;       // appended by shade for the next iteration
+    uint32_t n_free;       // slots released by shade
+    uint32_t ext_cursor;   // persistent-warp fetch cursor of extend
+    uint32_t done;
+    uint32_t pad;
+    uint32_t n_shade[Q_COUNT + 3];
+    unsigned long long next_work, total_work, gen_base;
+    unsigned long long rays, iterations;
+    VisitCounters visits;
+};
+
+struct RenderParams {
+    uint32_t w, h, npix, spp_begin, max_depth;
+    uint2 seed;
+};
+
+struct Pool {
+    float4* ray_o;   // origin.xyz, pixel
+    float4* ray_d;   // direction.xyz, sample
+    float4* thr;     // throughput.rgb, bounce
+    uint4* hit;      // t, prim ref, instance, material
+    uint32_t* q_ext[2];
+    uint32_t* q_shade;  // Q_COUNT queues of `slots` entries
+    uint32_t* free_list;
+    uint32_t slots;
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// one atomic per warp: every lane of the warp must call this (pred false = no entry). Returns the entry index.
+__device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
+    uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return 0;
+    uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane_id()) - 1u));
+}
+
+__device__ __forceinline__ void accumulate(long long* accum, uint32_t* nonfinite, uint32_t pixel, V3 c) {
+    const float kScale = 4294967296.0f;  // 2^32
+    float v[3] = {c.x, c.y, c.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (v[k] == 0.0f) continue;
+        if (!isfinite(v[k])) {
+            atomicOr(&nonfinite[pixel], 1u << k);  // the reference's f32 sum would be poisoned (main.rs:634)
+            continue;
+        }
+        atomicAdd(reinterpret_cast<unsigned long long*>(&accum[(size_t)pixel * 4 + k]), (unsigned long long)__float2ll_rn(v[k] * kScale));
+    }
+}
+
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+}
+
+__global__ void k_advance(QueueState* q) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    q->rays += q->n_ext;
+    uint32_t n_cont = q->n_next;
+    q->n_next = 0;
+    for (int k = 0; k < Q_COUNT; ++k) q->n_shade[k] = 0;
+    unsigned long long remaining = q->total_work - q->next_work;
+    uint32_t n_new = (uint32_t)min((unsigned long long)q->n_free, remaining);
+    q->gen_base = q->next_work;
+    q->next_work += n_new;
+    q->n_free = 0;
+    q->n_cont = n_cont;
+    q->n_new = n_new;
+    q->n_ext = n_cont + n_new;
+    q->ext_cursor = 0;
+    q->done = (n_cont + n_new == 0) ? 1u : 0u;
+    if (n_cont + n_new) q->iterations++;
+}
+
+// Camera::ray world.rs:53-63 with the pixel jitter of main.rs:258-259 (jitter == false: pixel centres, main.rs:189-190)
+__device__ __forceinline__ Ray camera_ray(const DCamera& cam, const RenderParams& rp, uint32_t pixel, uint32_t sample, bool jitter) {
+    uint32_t x = pixel % rp.w, y = pixel / rp.w;
+    RngKey key{pixel, sample, kBounceCamera, rp.seed};
+    Rand4 xi = draw4(key, kStreamScatter);
+    float s = jitter ? ((float)x + xi.x) / (float)(rp.w - 1) : (float)x / (float)(rp.w - 1);
+    float t = jitter ? ((float)y + xi.y) / (float)(rp.h - 1) : (float)y / (float)(rp.h - 1);
+    V3 blur = sample_unit_disk(xi.z, xi.w) * cam.lens_radius;
+    V3 offset = v3(cam.u) * blur.x + v3(cam.v) * blur.y;
+    Ray r;
+    r.o = v3(cam.origin) + offset;
+    r.d = v3(cam.llc) + (v3(cam.horizontal) * s) + (v3(cam.vertical) * t) - v3(cam.origin) - offset;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp, Pool pool,
+                                                  QueueState* q, int cur) {
+    const uint32_t n_new = q->n_new, n_cont = q->n_cont;
+    const unsigned long long base = q->gen_base;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
+        uint32_t slot = pool.free_list[i];
+        unsigned long long wk = base + i;
+        uint32_t pixel = (uint32_t)(wk % rp.npix);
+        uint32_t sample = rp.spp_begin + (uint32_t)(wk / rp.npix);
+        Ray r = camera_ray(cam, rp, pixel, sample, true);
+        pool.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
+        pool.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(sample));
+        pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+        pool.q_ext[cur][n_cont + i] = slot;
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
+                                                QueueState* q, int cur) {
+    const uint32_t n = q->n_ext;
+    const uint32_t* __restrict__ queue = pool.q_ext[cur];
+    VisitCounters cnt{0, 0, 0, 0, 0};
+    const float inf = __int_as_float(0x7f800000);
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(&q->ext_cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane_id();
+        const bool valid = i < n;
+        uint32_t slot = 0, kind = 0xFFu;
+        if (valid) {
+            slot = queue[i];
+            float4 o = pool.ray_o[slot], d = pool.ray_d[slot];
+            Ray r{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}};
+            RngKey key{__float_as_uint(o.w), __float_as_uint(d.w), 0u, rp.seed};
+            if (sc.n_volumes) key.bounce = __float_as_uint(pool.thr[slot].w);
+            HitRec h = traverse<COUNT>(sc, r, 0.001f, inf, key, &cnt);  // world.rs:68: [0.001, +inf)
+            int32_t m = -1;
+            kind = Q_MISS;
+            if (h.prim != kNone) {
+                m = hit_material(sc, h);
+                kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
+            }
+            pool.hit[slot] = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
+        }
+        // material-sorted shading queues: one atomic per (warp, kind)
+        uint32_t peers = __match_any_sync(0xffffffffu, kind);
+        if (valid) {
+            uint32_t leader = __ffs(peers) - 1;
+            uint32_t qbase = 0;
+            if (lane_id() == leader) qbase = atomicAdd(&q->n_shade[kind], __popc(peers));
+            qbase = __shfl_sync(peers, qbase, leader);
+            pool.q_shade[(size_t)kind * pool.slots + qbase + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
+        }
+    }
+    if (COUNT) {
+        unsigned long long v[5] = {cnt.node_visits, cnt.tri_tests, cnt.sphere_tests, cnt.instance_tests, cnt.volume_tests};
+        unsigned long long* dst = &q->visits.node_visits;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if (lane_id() == 0 && x) atomicAdd(&dst[k], x);
+        }
+    }
+}
+
+// One queue entry of Camera::trace's hit/miss handling (world.rs:69-77) in iterative form:
+// radiance += throughput * emitted; throughput *= attenuation.
+__device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams& rp, const Pool& pool, long long* accum, uint32_t* nonfinite,
+                                            uint32_t kind, uint32_t slot, bool& cont) {
+    float4 o = pool.ray_o[slot], d = pool.ray_d[slot], th = pool.thr[slot];
+    const uint32_t pixel = __float_as_uint(o.w), sample = __float_as_uint(d.w);
+    uint32_t bounce = __float_as_uint(th.w);
+    Ray ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}};
+    V3 thr{th.x, th.y, th.z};
+    cont = false;
+    if (kind == Q_MISS) {  // world.rs:77
+        accumulate(accum, nonfinite, pixel, thr * background(sc, ray));
+    } else {
+        uint4 hr = pool.hit[slot];
+        HitRec h{__uint_as_float(hr.x), hr.y, hr.z};
+        RngKey key{pixel, sample, bounce, rp.seed};
+        mrt_material mat = sc.materials[(int32_t)hr.w];
+        mrt_material emat = mat;
+        if (mat.kind == MRT_MAT_MIX) {  // Mix::emit and Mix::scatter flip independent coins (material.rs:403-417)
+            emat = pick_material(sc, (int32_t)hr.w, key, kStreamEmit);
+            mat = pick_material(sc, (int32_t)hr.w, key, kStreamMix);
+        }
+        Surfel s = resolve_hit(sc, ray, h, (int32_t)hr.w);
+        if (emat.kind == MRT_MAT_DIFFUSE_LIGHT) accumulate(accum, nonfinite, pixel, thr * V3{emat.p[0], emat.p[1], emat.p[2]});  // world.rs:69
+        ScatterOut sco;
+        scatter_kind(sc, mat, ray, s, draw4(key, kStreamScatter), sco);
+        if (sco.scattered) {
+            thr = thr * sco.attenuation;
+            bounce += 1;
+            if (bounce < rp.max_depth) {  // world.rs:66: the next call would be depth == 0 -> contributes 0
+                cont = true;
+                pool.ray_o[slot] = make_float4(s.point.x, s.point.y, s.point.z, o.w);
+                pool.ray_d[slot] = make_float4(sco.dir.x, sco.dir.y, sco.dir.z, d.w);
+                pool.thr[slot] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(bounce));
+            }
+        }
+    }
+    if (!cont && bounce)  // buffer.set(.., MAX_DEPTH - depth) main.rs:263, merged at :635
+        atomicAdd(reinterpret_cast<unsigned long long*>(&accum[(size_t)pixel * 4 + 3]), (unsigned long long)bounce);
+}
+
+__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
+                                               QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
+    uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
+    for (uint32_t kind = 0; kind < Q_COUNT; ++kind) {
+        const uint32_t n = q->n_shade[kind];
+        const uint32_t* __restrict__ queue = pool.q_shade + (size_t)kind * pool.slots;
+        const uint32_t n_round = (n + 31u) & ~31u;  // whole warps, so the ballots below see all 32 lanes
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+            const bool valid = i < n;
+            bool cont = false;
+            uint32_t slot = 0;
+            if (valid) {
+                slot = queue[i];
+                shade_entry(sc, rp, pool, accum, nonfinite, kind, slot, cont);
+            }
+            uint32_t at = warp_append(&q->n_next, valid && cont);
+            if (valid && cont) q_next[at] = slot;
+            at = warp_append(&q->n_free, valid && !cont);
+            if (valid && !cont) pool.free_list[at] = slot;
+        }
+    }
+}
+
+// PASS A (main.rs:166-222): Camera::albedo_normal (world.rs:81-93) at pixel centres
+__global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp,
+                                             float* albedo, float* normal, uint32_t* object_id, uint32_t* tri_id, float* t_out) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= rp.npix) return;
+    const float inf = __int_as_float(0x7f800000);
+    Ray ray = camera_ray(cam, rp, pixel, 0u, false);
+    RngKey key{pixel, 0u, 0u, rp.seed};
+    HitRec h = traverse<false>(sc, ray, 0.001f, inf, key, nullptr);
+    V3 a, n{0.0f, 0.0f, 0.0f};
+    uint32_t obj = kNone, tri = kNone;
+    float t = inf;
+    if (h.prim != kNone) {
+        int32_t m = hit_material(sc, h);
+        mrt_material mat = sc.materials[m], emat = mat;
+        if (mat.kind == MRT_MAT_MIX) {
+            emat = pick_material(sc, m, key, kStreamEmit);
+            mat = pick_material(sc, m, key, kStreamMix);
+        }
+        Surfel s = resolve_hit(sc, ray, h, m);
+        V3 emitted = (emat.kind == MRT_MAT_DIFFUSE_LIGHT) ? V3{emat.p[0], emat.p[1], emat.p[2]} : V3{0.0f, 0.0f, 0.0f};
+        ScatterOut sco;
+        scatter_kind(sc, mat, ray, s, draw4(key, kStreamScatter), sco);
+        a = sco.scattered ? sco.attenuation : emitted;
+        n = s.normal;
+        obj = s.object_id;
+        tri = s.tri_id;
+        t = h.t;
+    } else {
+        a = background(sc, ray);
+    }
+    if (albedo) { albedo[3 * (size_t)pixel] = a.x; albedo[3 * (size_t)pixel + 1] = a.y; albedo[3 * (size_t)pixel + 2] = a.z; }
+    if (normal) { normal[3 * (size_t)pixel] = n.x; normal[3 * (size_t)pixel + 1] = n.y; normal[3 * (size_t)pixel + 2] = n.z; }
+    if (object_id) object_id[pixel] = obj;
+    if (tri_id) tri_id[pixel] = tri;
+    if (t_out) t_out[pixel] = t;
+}
+
+// accumulators -> the reference's Image.pixels view: (sum colour f32, sum bounces u32)  main.rs:599
+__global__ void k_resolve_sums(const long long* accum, const uint32_t* nonfinite, uint32_t npix, float* sum_rgb, uint32_t* sum_bounces) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        uint32_t bad = nonfinite[p];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float v = (float)((double)accum[(size_t)p * 4 + k] * 2.3283064365386963e-10);  // * 2^-32
+            if (bad & (1u << k)) v = __int_as_float(0x7fc00000);
+            sum_rgb[(size_t)p * 3 + k] = v;
+        }
+        sum_bounces[p] = (uint32_t)accum[(size_t)p * 4 + 3];
+    }
+}
+
+// Image::to_rgb_bytes main.rs:640-722 (Default and Depth modes) with the row flip of Image::dump :763-768
+__global__ void k_resolve_rgb8(const long long* accum, const uint32_t* nonfinite, uint32_t w, uint32_t h, uint32_t count, int mode, int flip,
+                               uint32_t max_bounces, uint8_t* out) {
+    const uint32_t npix = w * h;
+    const float scale = 1.0f / (float)count;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        uint32_t y = p / w, x = p % w;
+        uint32_t dst = (flip ? (h - 1 - y) : y) * w + x;
+        float px[3];
+        if (count == 0) {
+            px[0] = px[1] = px[2] = 0.0f;
+        } else if (mode == 2) {  // Depth :655-665
+            float max_depth = (float)max(max_bounces, 1u) * scale;
+            float dpt = fminf(fmaxf(((float)(uint32_t)accum[(size_t)p * 4 + 3] * scale) / max_depth, 0.0f), 1.0f);
+            px[0] = px[1] = px[2] = dpt;
+        } else {  // Default :667-673
+            uint32_t bad = nonfinite[p];
+            for (int k = 0; k < 3; ++k) {
+                float v = (float)((double)accum[(size_t)p * 4 + k] * 2.3283064365386963e-10);
+                if (bad & (1u << k)) v = __int_as_float(0x7fc00000);
+                px[k] = fmaxf(fminf(powf(scale * v, 1.0f / 2.2f), 1.0f), 0.0f);  // NaN -> 1 (f32::min drops NaN)
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            float v = px[k] * 255.0f;
+            out[(size_t)dst * 3 + k] = (uint8_t)(v >= 255.0f ? 255 : (v > 0.0f ? (int)v : 0));  // `as u8` truncates and saturates
+        }
+    }
+}
+__global__ void k_max_bounces(const long long* accum, uint32_t npix, uint32_t* out) {
+    uint32_t m = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) m = max(m, (uint32_t)accum[(size_t)p * 4 + 3]);
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, off));
+    if (lane_id() == 0) atomicMax(out, m);
+}
+
+// test hooks (include/mrt_debug.h)
+__global__ void k_debug_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_10(ctr, key); }
+__global__ void k_debug_samplers(uint2 seed, uint32_t n, float* ball, float* sphere, float* disk) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        RngKey key{i, 0u, 0u, seed};
+        Rand4 xi = draw4(key, 0);
+        V3 b = sample_unit_ball(xi.x, xi.y, xi.z), s = sample_unit_vector(xi.x, xi.y), d = sample_unit_disk(xi.z, xi.w);
+        ball[3 * i] = b.x; ball[3 * i + 1] = b.y; ball[3 * i + 2] = b.z;
+        sphere[3 * i] = s.x; sphere[3 * i + 1] = s.y; sphere[3 * i + 2] = s.z;
+        disk[2 * i] = d.x; disk[2 * i + 1] = d.y;
+    }
+}
+
+}  // namespace mrt
+
+using namespace mrt;
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ---------------------------------------------------------------------------------------------------------------
+struct mrt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int n_sms = 0;
+    // scene
+    std::vector<void*> scene_allocs;
+    DScene scene{};
+    bool has_scene = false;
+    DCamera cam{};
+    bool has_camera = false;
+    uint64_t scene_bytes = 0;
+    // image
+    uint32_t w = 0, h = 0, count = 0;
+    long long* d_accum = nullptr;
+    uint32_t* d_nonfinite = nullptr;
+    // pool
+    Pool pool{};
+    QueueState* d_q = nullptr;
+    QueueState* h_q = nullptr;  // pinned, 2 status slots + 1 final
+    cudaEvent_t ev_status[2] = {nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // options
+    bool opt_count = false, opt_time = false;
+    uint64_t opt_pool_slots = 0;
+    mrt_stats stats{};
+    int grid_extend = 0, grid_extend_count = 0, grid_shade = 0, grid_generate = 0;
+};
+
+static std::string g_create_error;
+
+#define MRT_CUDA(call)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+            return MRT_E_CUDA;                                                                              \
+        }                                                                                                   \
+    } while (0)
+
+static int fail(mrt_context* ctx, int code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+template <class T>
+static int upload(mrt_context* ctx, const T* src, size_t n, const T** dst) {
+    *dst = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    void* p = nullptr;
+    MRT_CUDA(cudaMalloc(&p, bytes));
+    ctx->scene_allocs.push_back(p);
+    ctx->scene_bytes += bytes;
+    if (n) MRT_CUDA(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dst = static_cast<const T*>(p);
+    return MRT_OK;
+}
+
+static void free_scene(mrt_context* ctx) {
+    for (void* p : ctx->scene_allocs) cudaFree(p);
+    ctx->scene_allocs.clear();
+    ctx->scene_bytes = 0;
+    ctx->has_scene = false;
+}
+static void free_pool(mrt_context* ctx) {
+    Pool& p = ctx->pool;
+    cudaFree(p.ray_o); cudaFree(p.ray_d); cudaFree(p.thr); cudaFree(p.hit);
+    cudaFree(p.q_ext[0]); cudaFree(p.q_ext[1]); cudaFree(p.q_shade); cudaFree(p.free_list);
+    p = Pool{};
+}
+static void free_image(mrt_context* ctx) {
+    cudaFree(ctx->d_accum);
+    cudaFree(ctx->d_nonfinite);
+    ctx->d_accum = nullptr;
+    ctx->d_nonfinite = nullptr;
+    ctx->w = ctx->h = ctx->count = 0;
+}
+
+extern "C" {
+
+int mrt_abi_version(void) { return MRT_ABI_VERSION; }
+
+const char* mrt_last_error(mrt_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mrt_context_create(int device, void* stream, mrt_context** out) {
+    if (!out) { g_create_error = "out is NULL"; return MRT_E_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this backend has no CPU fallback)";
+        return MRT_E_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return MRT_E_INVALID; }
+    mrt_context* ctx = new mrt_context();
+    ctx->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return MRT_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        g_create_error = "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        delete ctx;
+        return MRT_E_UNSUPPORTED;
+    }
+    ctx->n_sms = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        ctx->own_stream = true;
+    }
+    if ((e = cudaMalloc(&ctx->d_q, sizeof(QueueState))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost(&ctx->h_q, 3 * sizeof(QueueState))) != cudaSuccess) return bail("cudaMallocHost", e);
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_status[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_begin)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return bail("cudaEventCreate", e);
+    // persistent grids: SM count x resident blocks per SM
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, 128, 0);
+    ctx->grid_extend = ctx->n_sms * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true>, 128, 0);
+    ctx->grid_extend_count = ctx->n_sms * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
+    ctx->grid_shade = ctx->n_sms * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_generate, 256, 0);
+    ctx->grid_generate = ctx->n_sms * std::max(occ, 1);
+    cudaDeviceSetLimit(cudaLimitStackSize, 2048);
+    *out = ctx;
+    return MRT_OK;
+}
+
+void mrt_context_destroy(mrt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_pool(ctx);
+    free_image(ctx);
+    cudaFree(ctx->d_q);
+    cudaFreeHost(ctx->h_q);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev_status[i]) cudaEventDestroy(ctx->ev_status[i]);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static bool ref_ok(const mrt_scene_desc* s, uint32_t ref, bool allow_node) {
+    uint32_t idx = MRT_REF_INDEX(ref);
+    switch (MRT_REF_KIND(ref)) {
+        case MRT_PRIM_NODE: return allow_node && idx < s->n_nodes;
+        case MRT_PRIM_SPHERE: return idx < s->n_spheres;
+        case MRT_PRIM_TRIANGLE: return idx < s->n_tris;
+        case MRT_PRIM_INSTANCE: return idx < s->n_instances;
+        case MRT_PRIM_VOLUME: return idx < s->n_volumes;
+        default: return false;
+    }
+}
+
+static void leaf_bounds(const mrt_scene_desc* s, uint32_t ref, float lo[3], float hi[3]) {
+    uint32_t idx = MRT_REF_INDEX(ref);
+    switch (MRT_REF_KIND(ref)) {
+        case MRT_PRIM_NODE:
+            for (int k = 0; k < 3; ++k) { lo[k] = s->nodes[idx].bmin[k]; hi[k] = s->nodes[idx].bmax[k]; }
+            break;
+        case MRT_PRIM_SPHERE: {
+            float r = std::fabs(s->spheres[idx].radius);
+            for (int k = 0; k < 3; ++k) { lo[k] = s->spheres[idx].center[k] - r; hi[k] = s->spheres[idx].center[k] + r; }
+            break;
+        }
+        case MRT_PRIM_TRIANGLE: {
+            const float* v = s->tri_verts + 9 * (size_t)idx;
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::fmin(std::fmin(v[k], v[3 + k]), v[6 + k]);
+                hi[k] = std::fmax(std::fmax(v[k], v[3 + k]), v[6 + k]);
+            }
+            break;
+        }
+        case MRT_PRIM_INSTANCE:
+            for (int k = 0; k < 3; ++k) { lo[k] = s->instances[idx].bmin[k]; hi[k] = s->instances[idx].bmax[k]; }
+            break;
+        case MRT_PRIM_VOLUME: leaf_bounds(s, s->volumes[idx].target, lo, hi); break;
+    }
+}
+
+// depth of the subtree under `ref` counted in inner nodes, iteratively; -1 on a malformed tree
+static int subtree_depth(const mrt_scene_desc* s, uint32_t root, bool tlas, std::string& why) {
+    if (MRT_REF_KIND(root) != MRT_PRIM_NODE) return 0;
+    struct Item { uint32_t ref; int depth; };
+    std::vector<Item> st;
+    st.push_back({root, 1});
+    int best = 0;
+    uint64_t visited = 0;
+    while (!st.empty()) {
+        Item it = st.back();
+        st.pop_back();
+        if (++visited > 2 * s->n_nodes + 2) { why = "node graph is not a tree"; return -1; }
+        best = std::max(best, it.depth);
+        const mrt_node& n = s->nodes[MRT_REF_INDEX(it.ref)];
+        const uint32_t ch[2] = {n.left, n.right};
+        for (int k = 0; k < 2; ++k) {
+            if (ch[k] == MRT_REF_NONE) {
+                if (k == 0) { why = "node without a left child"; return -1; }
+                continue;
+            }
+            if (!ref_ok(s, ch[k], true)) { why = "node child reference out of range"; return -1; }
+            uint32_t kind = MRT_REF_KIND(ch[k]);
+            if (kind == MRT_PRIM_NODE) st.push_back({ch[k], it.depth + 1});
+            else if (tlas && kind == MRT_PRIM_TRIANGLE) { why = "bare Triangle in the world list is not supported (wrap it in a Model)"; return -2; }
+            else if (!tlas && kind != MRT_PRIM_TRIANGLE) { why = "a BLAS may only contain triangles"; return -1; }
+        }
+    }
+    return best;
+}
+
+int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!s) return fail(ctx, MRT_E_INVALID, "scene is NULL");
+    if (s->abi_version != MRT_ABI_VERSION) return fail(ctx, MRT_E_INVALID, "mrt_scene_desc.abi_version mismatch");
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    // ---- validate ------------------------------------------------------------------------------------------
+    if (s->n_nodes >= (1ull << 29) || s->n_tris >= (1ull << 29) || s->n_spheres >= (1ull << 29) || s->n_instances >= (1ull << 29))
+        return fail(ctx, MRT_E_INVALID, "array too large for 29-bit primitive references");
+    for (uint32_t i = 0; i < s->n_roots; ++i) {
+        if (!ref_ok(s, s->roots[i], true)) return fail(ctx, MRT_E_INVALID, "root reference out of range");
+        if (MRT_REF_KIND(s->roots[i]) == MRT_PRIM_TRIANGLE) return fail(ctx, MRT_E_UNSUPPORTED, "bare Triangle in the world list is not supported (wrap it in a Model)");
+    }
+    auto mat_ok = [&](int32_t m, bool none_ok) { return (none_ok && m == -1) || (m >= 0 && (uint64_t)m < s->n_materials); };
+    auto surf_ok = [&](int32_t v) { return v >= 0 && (uint64_t)v < s->n_surfaces; };
+    for (uint64_t i = 0; i < s->n_surfaces; ++i) {
+        const mrt_surface& u = s->surfaces[i];
+        bool ok = true;
+        if (u.kind == MRT_SURF_TEXTURE) ok = u.a >= 0 && (uint64_t)u.a < s->n_textures;
+        else if (u.kind == MRT_SURF_YCBCR) ok = u.a >= 0 && (uint64_t)u.a < s->n_textures && u.b >= 0 && (uint64_t)u.b < s->n_textures;
+        else if (u.kind == MRT_SURF_BLEND) ok = surf_ok(u.a) && surf_ok(u.b) && (uint64_t)u.a < i && (uint64_t)u.b < i && u.mode >= 0 && u.mode <= 3;
+        else if (u.kind == MRT_SURF_FALLBACK) ok = surf_ok(u.a) && (uint64_t)u.a < i;
+        else if (u.kind != MRT_SURF_SOLID) ok = false;
+        if (!ok) return fail(ctx, MRT_E_INVALID, "malformed surface table entry " + std::to_string(i));
+    }
+    for (uint64_t i = 0; i < s->n_textures; ++i) {
+        const mrt_texture& t = s->textures[i];
+        if (t.width == 0 || t.height == 0 || t.texel_offset + (uint64_t)t.width * t.height > s->n_texels) return fail(ctx, MRT_E_INVALID, "texture outside the texel array");
+        if (t.wrap != MRT_WRAP_REPEAT && t.wrap != MRT_WRAP_CLAMP) return fail(ctx, MRT_E_UNSUPPORTED, "Mirror wrapping is not implemented (texture.rs:280)");
+    }
+    for (uint64_t i = 0; i < s->n_materials; ++i) {
+        const mrt_material& m = s->materials[i];
+        bool ok = m.kind >= 0 && m.kind < MRT_MAT_KINDS;
+        if (ok && (m.kind == MRT_MAT_LAMBERTIAN || m.kind == MRT_MAT_METAL || m.kind == MRT_MAT_SPECULAR)) ok = surf_ok(m.surface);
+        if (ok && m.kind == MRT_MAT_MIX) ok = mat_ok(m.left, false) && mat_ok(m.right, false) && (uint64_t)m.left < i && (uint64_t)m.right < i;
+        if (!ok) return fail(ctx, MRT_E_INVALID, "malformed material table entry " + std::to_string(i));
+    }
+    for (uint64_t i = 0; i < s->n_spheres; ++i)
+        if (!mat_ok(s->spheres[i].material, false)) return fail(ctx, MRT_E_INVALID, "sphere material out of range");
+    for (uint64_t i = 0; i < s->n_tris; ++i)
+        if (!mat_ok(s->tri_shading[i].material, false)) return fail(ctx, MRT_E_INVALID, "triangle material out of range");
+    for (uint64_t i = 0; i < s->n_volumes; ++i) {
+        const mrt_volume& v = s->volumes[i];
+        if (!ref_ok(s, v.target, false)) return fail(ctx, MRT_E_INVALID, "volume target out of range");
+        if (MRT_REF_KIND(v.target) != MRT_PRIM_SPHERE) return fail(ctx, MRT_E_UNSUPPORTED, "only Volume<Sphere> is implemented");
+        if (!mat_ok(v.material, false)) return fail(ctx, MRT_E_INVALID, "volume material out of range");
+    }
+    if (s->background.kind == MRT_BG_SKYSPHERE && !surf_ok(s->background.surface[0])) return fail(ctx, MRT_E_INVALID, "background surface out of range");
+    if (s->background.kind == MRT_BG_CUBEMAP)
+        for (int k = 0; k < 6; ++k)
+            if (!surf_ok(s->background.surface[k])) return fail(ctx, MRT_E_INVALID, "background surface out of range");
+    std::string why;
+    int blas_depth = 0;
+    for (uint64_t i = 0; i < s->n_blas; ++i) {
+        const mrt_blas& b = s->blas[i];
+        if (MRT_REF_KIND(b.root) != MRT_PRIM_NODE || MRT_REF_INDEX(b.root) >= s->n_nodes || (uint64_t)b.first_tri + b.n_tris > s->n_tris)
+            return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
+        int d = subtree_depth(s, b.root, false, why);
+        if (d < 0) return fail(ctx, MRT_E_INVALID, why);
+        blas_depth = std::max(blas_depth, d);
+    }
+    for (uint64_t i = 0; i < s->n_instances; ++i) {
+        if (s->instances[i].blas >= s->n_blas) return fail(ctx, MRT_E_INVALID, "instance BLAS out of range");
+        if (!mat_ok(s->instances[i].material, true)) return fail(ctx, MRT_E_INVALID, "instance material out of range");
+    }
+    int tlas_depth = 0;
+    for (uint32_t i = 0; i < s->n_roots; ++i) {
+        int d = subtree_depth(s, s->roots[i], true, why);
+        if (d == -2) return fail(ctx, MRT_E_UNSUPPORTED, why);
+        if (d < 0) return fail(ctx, MRT_E_INVALID, why);
+        tlas_depth = std::max(tlas_depth, d);
+    }
+    if (tlas_depth + blas_depth + 2 + (int)std::min<uint32_t>(s->n_roots, 8) > kStackSize)
+        return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack");
+
+    // ---- re-layout and copy ----------------------------------------------------------------------------------
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    DScene d{};
+    std::vector<DNode> nodes(s->n_nodes);
+    const float inf = INFINITY;
+    for (uint64_t i = 0; i < s->n_nodes; ++i) {
+        const mrt_node& n = s->nodes[i];
+        float l0[3], h0[3], l1[3] = {inf, inf, inf}, h1[3] = {-inf, -inf, -inf};
+        leaf_bounds(s, n.left, l0, h0);
+        if (n.right != MRT_REF_NONE) leaf_bounds(s, n.right, l1, h1);
+        DNode& o = nodes[i];
+        o.xy0 = make_float4(l0[0], h0[0], l0[1], h0[1]);
+        o.xy1 = make_float4(l1[0], h1[0], l1[1], h1[1]);
+        o.z01 = make_float4(l0[2], h0[2], l1[2], h1[2]);
+        o.child0 = n.left;
+        o.child1 = n.right;
+        o.pad0 = o.pad1 = 0;
+    }
+    std::vector<float4> spheres(s->n_spheres);
+    std::vector<DSphereAux> saux(s->n_spheres);
+    for (uint64_t i = 0; i < s->n_spheres; ++i) {
+        spheres[i] = make_float4(s->spheres[i].center[0], s->spheres[i].center[1], s->spheres[i].center[2], s->spheres[i].radius);
+        saux[i] = DSphereAux{s->spheres[i].material, s->spheres[i].object_id};
+    }
+    std::vector<DTriVerts> tv(s->n_tris);
+    for (uint64_t i = 0; i < s->n_tris; ++i) {
+        const float* v = s->tri_verts + 9 * i;
+        tv[i].a = make_float4(v[0], v[1], v[2], 0.0f);
+        tv[i].b = make_float4(v[3], v[4], v[5], 0.0f);
+        tv[i].c = make_float4(v[6], v[7], v[8], 0.0f);
+    }
+    std::vector<DInstance> inst(s->n_instances);
+    for (uint64_t i = 0; i < s->n_instances; ++i) {
+        const mrt_instance& in = s->instances[i];
+        auto pack = [](const float* m, float4& a, float4& b, float4& c) {  // columns c0.xyz c1.xyz c2.xyz c3.xyz
+            a = make_float4(m[0], m[1], m[2], m[4]);
+            b = make_float4(m[5], m[6], m[8], m[9]);
+            c = make_float4(m[10], m[12], m[13], m[14]);
+        };
+        DInstance& o = inst[i];
+        std::memset(&o, 0, sizeof o);
+        pack(in.inv_transform, o.inv0, o.inv1, o.inv2);
+        pack(in.transform, o.fwd0, o.fwd1, o.fwd2);
+        o.root = s->blas[in.blas].root;
+        o.material = in.material;
+        o.flags = in.flags;
+        o.object_id = in.object_id;
+        o.pad[0] = in.blas;
+    }
+    int rc;
+    if ((rc = upload(ctx, nodes.data(), nodes.size(), &d.nodes))) return rc;
+    if ((rc = upload(ctx, spheres.data(), spheres.size(), &d.spheres))) return rc;
+    if ((rc = upload(ctx, saux.data(), saux.size(), &d.sphere_aux))) return rc;
+    if ((rc = upload(ctx, tv.data(), tv.size(), &d.tri_verts))) return rc;
+    if ((rc = upload(ctx, s->tri_shading, (size_t)s->n_tris, &d.tri_shading))) return rc;
+    if ((rc = upload(ctx, inst.data(), inst.size(), &d.instances))) return rc;
+    if ((rc = upload(ctx, s->blas, (size_t)s->n_blas, &d.blas))) return rc;
+    if ((rc = upload(ctx, s->volumes, (size_t)s->n_volumes, &d.volumes))) return rc;
+    if ((rc = upload(ctx, s->materials, (size_t)s->n_materials, &d.materials))) return rc;
+    if ((rc = upload(ctx, s->surfaces, (size_t)s->n_surfaces, &d.surfaces))) return rc;
+    if ((rc = upload(ctx, s->textures, (size_t)s->n_textures, &d.textures))) return rc;
+    if ((rc = upload(ctx, reinterpret_cast<const float4*>(s->texels), (size_t)s->n_texels, &d.texels))) return rc;
+    d.n_roots = s->n_roots;
+    d.n_volumes = (uint32_t)s->n_volumes;
+    d.roots_ext = nullptr;
+    if (s->n_roots <= 8) {
+        for (uint32_t i = 0; i < s->n_roots; ++i) d.roots[i] = s->roots[i];
+    } else if ((rc = upload(ctx, s->roots, (size_t)s->n_roots, &d.roots_ext))) {
+        return rc;
+    }
+    d.bg = s->background;
+    MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
+    ctx->scene = d;
+    ctx->has_scene = true;
+    return MRT_OK;
+}
+
+int mrt_camera_set(mrt_context* ctx, const mrt_camera* c) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!c) return fail(ctx, MRT_E_INVALID, "camera is NULL");
+    DCamera& d = ctx->cam;
+    d.origin = make_float3(c->origin[0], c->origin[1], c->origin[2]);
+    d.llc = make_float3(c->lower_left_corner[0], c->lower_left_corner[1], c->lower_left_corner[2]);
+    d.horizontal = make_float3(c->horizontal[0], c->horizontal[1], c->horizontal[2]);
+    d.vertical = make_float3(c->vertical[0], c->vertical[1], c->vertical[2]);
+    d.u = make_float3(c->u[0], c->u[1], c->u[2]);
+    d.v = make_float3(c->v[0], c->v[1], c->v[2]);
+    d.lens_radius = c->lens_radius;
+    ctx->has_camera = true;
+    return MRT_OK;
+}
+
+static int check_ready(mrt_context* ctx) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!ctx->has_scene) return fail(ctx, MRT_E_STATE, "no scene uploaded (mrt_scene_upload)");
+    if (!ctx->has_camera) return fail(ctx, MRT_E_STATE, "no camera set (mrt_camera_set)");
+    return MRT_OK;
+}
+
+int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, float* albedo, float* normal, uint32_t* object_id, uint32_t* tri_id,
+                   float* t) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (w < 2 || h < 2 || (uint64_t)w * h > 0x7FFFFFFFull) return fail(ctx, MRT_E_INVALID, "image size out of range");
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)w * h;
+    float *d_alb = nullptr, *d_nrm = nullptr, *d_t = nullptr;
+    uint32_t *d_obj = nullptr, *d_tri = nullptr;
+    auto cleanup = [&]() { cudaFree(d_alb); cudaFree(d_nrm); cudaFree(d_t); cudaFree(d_obj); cudaFree(d_tri); };
+#define AOV_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MRT_E_CUDA; } } while (0)
+    if (albedo) AOV_TRY(cudaMalloc(&d_alb, npix * 12));
+    if (normal) AOV_TRY(cudaMalloc(&d_nrm, npix * 12));
+    if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
+    if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
+    if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))};
+    k_aov<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    AOV_TRY(cudaGetLastError());
+    if (albedo) AOV_TRY(cudaMemcpyAsync(albedo, d_alb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal) AOV_TRY(cudaMemcpyAsync(normal, d_nrm, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t) AOV_TRY(cudaMemcpyAsync(t, d_t, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (object_id) AOV_TRY(cudaMemcpyAsync(object_id, d_obj, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tri_id) AOV_TRY(cudaMemcpyAsync(tri_id, d_tri, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    AOV_TRY(cudaStreamSynchronize(ctx->stream));
+#undef AOV_TRY
+    cleanup();
+    return MRT_OK;
+}
+
+int mrt_accum_reset(mrt_context* ctx, uint32_t w, uint32_t h) {
+    if (!ctx) return MRT_E_INVALID;
+    if (w < 2 || h < 2 || (uint64_t)w * h > 0x7FFFFFFFull) return fail(ctx, MRT_E_INVALID, "image size out of range");
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->w != w || ctx->h != h || !ctx->d_accum) {
+        cudaStreamSynchronize(ctx->stream);
+        free_image(ctx);
+        MRT_CUDA(cudaMalloc(&ctx->d_accum, (size_t)w * h * 4 * sizeof(long long)));
+        MRT_CUDA(cudaMalloc(&ctx->d_nonfinite, (size_t)w * h * sizeof(uint32_t)));
+        ctx->w = w;
+        ctx->h = h;
+    }
+    MRT_CUDA(cudaMemsetAsync(ctx->d_accum, 0, (size_t)w * h * 4 * sizeof(long long), ctx->stream));  // image.clear() main.rs:233
+    MRT_CUDA(cudaMemsetAsync(ctx->d_nonfinite, 0, (size_t)w * h * sizeof(uint32_t), ctx->stream));
+    ctx->count = 0;
+    return MRT_OK;
+}
+
+static int ensure_pool(mrt_context* ctx, uint64_t total_work) {
+    uint64_t want = ctx->opt_pool_slots ? ctx->opt_pool_slots : (1ull << 22);
+    want = std::min<uint64_t>(want, std::max<uint64_t>((total_work + 1023) / 1024 * 1024, 1024));
+    want = std::min<uint64_t>(want, 1ull << 28);
+    if (ctx->pool.slots == want) return MRT_OK;
+    cudaStreamSynchronize(ctx->stream);
+    free_pool(ctx);
+    Pool& p = ctx->pool;
+    MRT_CUDA(cudaMalloc(&p.ray_o, want * 16));
+    MRT_CUDA(cudaMalloc(&p.ray_d, want * 16));
+    MRT_CUDA(cudaMalloc(&p.thr, want * 16));
+    MRT_CUDA(cudaMalloc(&p.hit, want * 16));
+    MRT_CUDA(cudaMalloc(&p.q_ext[0], want * 4));
+    MRT_CUDA(cudaMalloc(&p.q_ext[1], want * 4));
+    MRT_CUDA(cudaMalloc(&p.q_shade, want * 4 * Q_COUNT));
+    MRT_CUDA(cudaMalloc(&p.free_list, want * 4));
+    p.slots = (uint32_t)want;
+    return MRT_OK;
+}
+
+int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_count, uint32_t max_depth, uint64_t seed) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!ctx->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
+    if (max_depth == 0) return fail(ctx, MRT_E_INVALID, "max_depth must be >= 1");
+    if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, MRT_E_INVALID, "sample range overflows 32 bits");
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t npix = ctx->w * ctx->h;
+    const uint64_t total = (uint64_t)npix * spp_count;
+    mrt_stats& st = ctx->stats;
+    st.paths = total; st.rays = 0; st.node_visits = st.tri_tests = st.sphere_tests = st.instance_tests = st.volume_tests = 0;
+    st.iterations = st.extend_launches = st.kernel_launches = 0;
+    st.render_ms = st.extend_ms = st.shade_ms = st.generate_ms = 0.0f;
+    st.scene_bytes = ctx->scene_bytes;
+    if (total == 0) { st.pool_slots = ctx->pool.slots; return MRT_OK; }
+    if ((rc = ensure_pool(ctx, total))) return rc;
+    st.pool_slots = ctx->pool.slots;
+    Pool pool = ctx->pool;
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))};
+
+    QueueState init;
+    std::memset(&init, 0, sizeof init);
+    init.n_free = pool.slots;
+    init.total_work = total;
+    ctx->h_q[2] = init;
+    MRT_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    MRT_CUDA(cudaMemcpyAsync(ctx->d_q, &ctx->h_q[2], sizeof(QueueState), cudaMemcpyHostToDevice, ctx->stream));
+    k_iota<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(pool.free_list, pool.slots);
+    st.kernel_launches++;
+
+    std::vector<cudaEvent_t> tev;  // 6 events per iteration when kernel timing is on
+    const int kChunk = 8;
+    int cur = 0;
+    auto launch_chunk = [&](int slot) -> int {
+        for (int it = 0; it < kChunk; ++it) {
+            cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (ctx->opt_time)
+                for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
+            k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q);
+            if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[0], ctx->stream));
+            k_generate<<<ctx->grid_generate, 256, 0, ctx->stream>>>(ctx->cam, rp, pool, ctx->d_q, cur);
+            if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[1], ctx->stream)); MRT_CUDA(cudaEventRecord(e[2], ctx->stream)); }
+            if (ctx->opt_count) k_extend<true><<<ctx->grid_extend_count, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            else k_extend<false><<<ctx->grid_extend, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
+            k_shade<<<ctx->grid_shade, 256, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+            if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));
+            cur ^= 1;
+            st.kernel_launches += 4;
+            st.extend_launches += 1;
+        }
+        MRT_CUDA(cudaGetLastError());
+        MRT_CUDA(cudaMemcpyAsync(&ctx->h_q[slot], ctx->d_q, sizeof(QueueState), cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(cudaEventRecord(ctx->ev_status[slot], ctx->stream));
+        return MRT_OK;
+    };
+    // keep one chunk of iterations queued ahead of the one whose status is being read, so the stream never idles
+    if ((rc = launch_chunk(0))) return rc;
+    for (int c = 0;; ++c) {
+        if ((rc = launch_chunk((c + 1) & 1))) return rc;
+        MRT_CUDA(cudaEventSynchronize(ctx->ev_status[c & 1]));
+        if (ctx->h_q[c & 1].done) break;
+    }
+    MRT_CUDA(cudaMemcpyAsync(&ctx->h_q[2], ctx->d_q, sizeof(QueueState), cudaMemcpyDeviceToHost, ctx->stream));
+    MRT_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    MRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    MRT_CUDA(cudaEventElapsedTime(&st.render_ms, ctx->ev_begin, ctx->ev_end));
+    const QueueState& fin = ctx->h_q[2];
+    st.rays = fin.rays + fin.n_ext;
+    st.iterations = fin.iterations;
+    st.node_visits = fin.visits.node_visits;
+    st.tri_tests = fin.visits.tri_tests;
+    st.sphere_tests = fin.visits.sphere_tests;
+    st.instance_tests = fin.visits.instance_tests;
+    st.volume_tests = fin.visits.volume_tests;
+    if (ctx->opt_time) {
+        for (size_t i = 0; i + 5 < tev.size(); i += 6) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, tev[i], tev[i + 1]) == cudaSuccess) st.generate_ms += ms;
+            if (cudaEventElapsedTime(&ms, tev[i + 2], tev[i + 3]) == cudaSuccess) st.extend_ms += ms;
+            if (cudaEventElapsedTime(&ms, tev[i + 4], tev[i + 5]) == cudaSuccess) st.shade_ms += ms;
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
+    ctx->count += spp_count;
+    return MRT_OK;
+}
+
+int mrt_accum_device_ptr(mrt_context* ctx, void** accum_i64, uint64_t* n_elems) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!ctx->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
+    if (accum_i64) *accum_i64 = ctx->d_accum;
+    if (n_elems) *n_elems = (uint64_t)ctx->w * ctx->h * 4;
+    return MRT_OK;
+}
+
+int mrt_accum_download(mrt_context* ctx, float* sum_rgb, uint32_t* sum_bounces, uint32_t* out_count) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!ctx->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)ctx->w * ctx->h;
+    float* d_rgb = nullptr;
+    uint32_t* d_b = nullptr;
+    MRT_CUDA(cudaMalloc(&d_rgb, npix * 12));
+    cudaError_t e = cudaMalloc(&d_b, npix * 4);
+    if (e != cudaSuccess) { cudaFree(d_rgb); return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e)); }
+    k_resolve_sums<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_accum, ctx->d_nonfinite, (uint32_t)npix, d_rgb, d_b);
+    if (sum_rgb) cudaMemcpyAsync(sum_rgb, d_rgb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream);
+    if (sum_bounces) cudaMemcpyAsync(sum_bounces, d_b, npix * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rgb);
+    cudaFree(d_b);
+    if (e != cudaSuccess) return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e));
+    if (out_count) *out_count = ctx->count;
+    return MRT_OK;
+}
+
+int mrt_render(mrt_context* ctx, uint32_t w, uint32_t h, uint32_t spp_begin, uint32_t spp_count, uint32_t max_depth, uint64_t seed, float* sum_rgb,
+               uint32_t* sum_bounces, uint32_t* out_count) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if ((rc = mrt_accum_reset(ctx, w, h))) return rc;
+    if ((rc = mrt_render_accumulate(ctx, spp_begin, spp_count, max_depth, seed))) return rc;
+    return mrt_accum_download(ctx, sum_rgb, sum_bounces, out_count);
+}
+
+int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8_t* out) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!ctx->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
+    if (!out) return fail(ctx, MRT_E_INVALID, "out is NULL");
+    if (mode != 0 && mode != 1 && mode != 2) return fail(ctx, MRT_E_UNSUPPORTED, "only Default(0), Denoise(1, as Default) and Depth(2) are resolved on the device");
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)ctx->w * ctx->h;
+    uint8_t* d_out = nullptr;
+    uint32_t* d_max = nullptr;
+    MRT_CUDA(cudaMalloc(&d_out, npix * 3));
+    cudaError_t e = cudaMalloc(&d_max, 4);
+    if (e != cudaSuccess) { cudaFree(d_out); return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e)); }
+    cudaMemsetAsync(d_max, 0, 4, ctx->stream);
+    uint32_t h_max = 0;
+    if (mode == 2) {
+        k_max_bounces<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_accum, (uint32_t)npix, d_max);
+        cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    k_resolve_rgb8<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_accum, ctx->d_nonfinite, ctx->w, ctx->h, count, mode == 2 ? 2 : 0, flip, h_max, d_out);
+    cudaMemcpyAsync(out, d_out, npix * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    cudaFree(d_max);
+    if (e != cudaSuccess) return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e));
+    return MRT_OK;
+}
+
+int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
+    if (!ctx) return MRT_E_INVALID;
+    switch (option) {
+        case MRT_OPT_COUNT_VISITS: ctx->opt_count = value != 0; return MRT_OK;
+        case MRT_OPT_TIME_KERNELS: ctx->opt_time = value != 0; return MRT_OK;
+        case MRT_OPT_POOL_SLOTS:
+            if (value != 0 && (value < 1024 || value > (1ull << 28))) return fail(ctx, MRT_E_INVALID, "pool slots out of range [1024, 2^28]");
+            ctx->opt_pool_slots = value / 1024 * 1024;
+            return MRT_OK;
+        default: return fail(ctx, MRT_E_INVALID, "unknown option");
+    }
+}
+
+int mrt_get_stats(mrt_context* ctx, mrt_stats* out) {
+    if (!ctx || !out) return MRT_E_INVALID;
+    *out = ctx->stats;
+    return MRT_OK;
+}
+
+int mrt_synchronize(mrt_context* ctx) {
+    if (!ctx) return MRT_E_INVALID;
+    MRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MRT_OK;
+}
+
+// ---- test hooks ---------------------------------------------------------------------------------------------------
+int mrt_debug_philox(mrt_context* ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!ctx) return MRT_E_INVALID;
+    uint4* d = nullptr;
+    MRT_CUDA(cudaMalloc(&d, sizeof(uint4)));
+    k_debug_philox<<<1, 1, 0, ctx->stream>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+    cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e));
+    return MRT_OK;
+}
+int mrt_debug_samplers(mrt_context* ctx, uint64_t seed, uint32_t n, float* in_ball3, float* unit_vec3, float* in_disk2) {
+    if (!ctx) return MRT_E_INVALID;
+    float *b = nullptr, *s = nullptr, *d = nullptr;
+    MRT_CUDA(cudaMalloc(&b, (size_t)n * 12));
+    MRT_CUDA(cudaMalloc(&s, (size_t)n * 12));
+    MRT_CUDA(cudaMalloc(&d, (size_t)n * 8));
+    k_debug_samplers<<<ctx->n_sms * 2, 256, 0, ctx->stream>>>(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), n, b, s, d);
+    cudaMemcpyAsync(in_ball3, b, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(unit_vec3, s, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(in_disk2, d, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(b); cudaFree(s); cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e));
+    return MRT_OK;
+}
+
+}  // extern "C"

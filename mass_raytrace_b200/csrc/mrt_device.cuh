@@ -1,0 +1,642 @@
+// mrt_device.cuh — device-side scene layout, Philox, intersection, traversal and shading for sm_100a.
+//
+// Arithmetic contract: every value that decides a hit or ends up in a hit record (ray transforms, sphere and
+// triangle tests, hit point, interpolated normal, face forwarding) is computed in the reference's f32 operation
+// order with IEEE add/mul/div/sqrt and NO fused multiply-add (this TU is compiled with -fmad=false, default
+// -prec-div/-prec-sqrt, no fast-math), so primary-ray t / normal / ids are bit-identical to the CPU restatement.
+// Only the AABB slab test deviates: it multiplies by a per-ray reciprocal instead of dividing (geom.rs:219-220
+// divides) and widens the interval by 4 ulp so that it never rejects a box the reference's test accepts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mrt.h"
+
+namespace mrt {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kSentinel = 0xFFFFFFFEu;  // stack marker: leave the current instance, restore the world ray
+constexpr int kStackSize = 64;
+
+// ---- device scene (HBM layout; all arrays 16-byte aligned, fetched with 128-bit loads) -----------------------
+// Inner node, 64 B = one half cache line: both children's AABBs + both child refs, so one fetch decides both
+// subtrees (the reference stores one AABB per node and tests it after the pointer chase, geom.rs:103-107, 186-187).
+struct __align__(16) DNode {
+    float4 xy0;  // child0: min.x max.x min.y max.y
+    float4 xy1;  // child1: min.x max.x min.y max.y
+    float4 z01;  // child0 min.z max.z, child1 min.z max.z
+    uint32_t child0, child1, pad0, pad1;  // prim refs (MRT_REF); kNone = absent
+};
+struct __align__(16) DTriVerts {
+    float4 a, b, c;  // vertex_a/b/c, w unused
+};
+struct __align__(16) DInstance {
+    float4 inv0, inv1, inv2;  // inv_transform columns c0.xyz c1.xyz c2.xyz c3.xyz packed as 12 floats
+    float4 fwd0, fwd1, fwd2;  // transform, same packing
+    uint32_t root;            // BLAS root ref
+    int32_t material;         // override or -1
+    uint32_t flags;
+    uint32_t object_id;
+    uint32_t pad[4];
+};
+struct DSphereAux {
+    int32_t material;
+    uint32_t object_id;
+};
+struct DScene {
+    const DNode* nodes;
+    const float4* spheres;  // center.xyz, radius
+    const DSphereAux* sphere_aux;
+    const DTriVerts* tri_verts;
+    const mrt_tri_shading* tri_shading;
+    const DInstance* instances;
+    const mrt_blas* blas;
+    const mrt_volume* volumes;
+    const mrt_material* materials;
+    const mrt_surface* surfaces;
+    const mrt_texture* textures;
+    const float4* texels;
+    uint32_t roots[8];
+    uint32_t n_roots;
+    uint32_t n_volumes;
+    const uint32_t* roots_ext;  // when n_roots > 8
+    mrt_background bg;
+};
+struct DCamera {
+    float3 origin, llc, horizontal, vertical, u, v;
+    float lens_radius;
+};
+
+struct VisitCounters {
+    unsigned long long node_visits, tri_tests, sphere_tests, instance_tests, volume_tests;
+};
+
+// ---- f32 vector helpers in the reference's operation order (math/generic.rs) ---------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 v3(float4 a) { return V3{a.x, a.y, a.z}; }
+__device__ __forceinline__ V3 v3(float3 a) { return V3{a.x, a.y, a.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return V3{a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // generic.rs:8-10
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {                                               // generic.rs:12-18
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float length_squared(V3 a) { return dot(a, a); }
+__device__ __forceinline__ float length(V3 a) { return sqrtf(length_squared(a)); }
+__device__ __forceinline__ V3 unit(V3 a) { return a / length(a); }  // math.rs:75-77
+__device__ __forceinline__ bool near_zero(V3 a) { return fabsf(a.x) <= 0.00001f && fabsf(a.y) <= 0.00001f && fabsf(a.z) <= 0.00001f; }
+__device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - (n * dot(v, n) * 2.0f); }  // math.rs:115-117
+__device__ __forceinline__ V3 refract(V3 v, V3 n, float eta) {                            // math.rs:119-124
+    float cos_theta = fminf(dot(-v, n), 1.0f);
+    V3 perp = (v + n * cos_theta) * eta;
+    V3 par = n * (-sqrtf(fabsf(1.0f - length_squared(perp))));
+    return perp + par;
+}
+// M4::transform (generic.rs:105-115) on the packed 3x4: ((c0*x + c1*y) + c2*z) + c3*w
+__device__ __forceinline__ V3 xform(float4 m0, float4 m1, float4 m2, V3 p, float w) {
+    return V3{((m0.x * p.x + m0.w * p.y) + m1.z * p.z) + m2.y * w,
+              ((m0.y * p.x + m1.x * p.y) + m1.w * p.z) + m2.z * w,
+              ((m0.z * p.x + m1.y * p.y) + m2.x * p.z) + m2.w * w};
+}
+
+struct Ray {
+    V3 o, d;
+};
+__device__ __forceinline__ V3 ray_at(const Ray& r, float t) { return r.o + (r.d * t); }  // world.rs:179-181
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (pixel, sample, bounce, stream), key = seed -----------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-8f; }  // [0,1), 24 bits
+struct Rand4 {
+    float x, y, z, w;
+};
+enum : uint32_t { kStreamScatter = 0, kStreamVolume = 0x100, kStreamMix = 0x200, kStreamEmit = 0x300, kStreamAlpha = 0x400 };
+constexpr uint32_t kBounceCamera = 0xFFFFFFFFu;
+struct RngKey {
+    uint32_t pixel, sample, bounce;
+    uint2 seed;
+};
+__device__ __forceinline__ Rand4 draw4(const RngKey& k, uint32_t stream) {
+    uint4 r = philox4x32_10(make_uint4(k.pixel, k.sample, k.bounce, stream), k.seed);
+    return Rand4{u01(r.x), u01(r.y), u01(r.z), u01(r.w)};
+}
+// Closed-form samplers with the same distributions as the reference's rejection loops (math.rs:80-109):
+// uniform in the unit disk, uniform on the unit sphere, uniform in the unit ball.
+__device__ __forceinline__ V3 sample_unit_disk(float a, float b) {
+    float s, c;
+    sincospif(2.0f * b, &s, &c);
+    float r = sqrtf(a);
+    return V3{r * c, r * s, 0.0f};
+}
+__device__ __forceinline__ V3 sample_unit_vector(float a, float b) {
+    float z = 1.0f - 2.0f * a;
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    sincospif(2.0f * b, &s, &c);
+    return V3{r * c, r * s, z};
+}
+__device__ __forceinline__ V3 sample_unit_ball(float a, float b, float c3) { return sample_unit_vector(a, b) * cbrtf(c3); }
+
+// ---- primitive tests -----------------------------------------------------------------------------------------
+// Sphere::intersect geom.rs:57-93 (t only; normal/point are recomputed for the closest hit by resolve_hit)
+__device__ __forceinline__ bool sphere_test(float4 s, const Ray& r, float t_min, float t_max, float& t_out) {
+    V3 oc = r.o - v3(s);
+    float a = length_squared(r.d);
+    float half_b = dot(oc, r.d);
+    float c = length_squared(oc) - (s.w * s.w);
+    float disc = (half_b * half_b) - (a * c);
+    if (disc < 0.0f) return false;
+    float sqrt_d = sqrtf(disc);
+    float root = (-half_b - sqrt_d) / a;
+    if (root < t_min || t_max < root) {
+        root = (-half_b + sqrt_d) / a;
+        if (root < t_min || t_max < root) return false;
+    }
+    t_out = root;
+    return true;
+}
+// Triangle::intersect geom.rs:504-533 (Moller-Trumbore part; the area-barycentric tail runs once, in resolve_hit)
+__device__ __forceinline__ bool triangle_test(const DTriVerts& tv, const Ray& r, float t_min, float t_max, float& t_out) {
+    V3 va = v3(tv.a), vb = v3(tv.b), vc = v3(tv.c);
+    V3 ab = vb - va, ac = vc - va;
+    V3 p_vec = cross(r.d, ac);
+    float det = dot(ab, p_vec);
+    if (fabsf(det) < 0.000001f) return false;
+    float inv_det = 1.0f / det;
+    V3 t_vec = r.o - va;
+    float u = dot(t_vec, p_vec) * inv_det;
+    if (u < 0.0f || u > 1.0f) return false;
+    V3 q_vec = cross(t_vec, ab);
+    float v = dot(r.d, q_vec) * inv_det;
+    if (v < 0.0f || v + u > 1.0f) return false;
+    float t = dot(ac, q_vec) * inv_det;
+    if (t < t_min || t > t_max) return false;
+    t_out = t;
+    return true;
+}
+
+// BoundingBox::hit geom.rs:218-247 for two boxes at once. NaN handling follows f32::min/max (= fminf/fmaxf).
+// (b - o) * inv_d keeps the reference's inf/NaN pattern for d == 0 (0 * inf = NaN like 0 / 0; x * inf = x / 0).
+__device__ __forceinline__ void slab2(const DNode& n, V3 o, V3 id, float t_min, float t_max, bool& h0, bool& h1, float& n0, float& n1) {
+    const float kWiden = 4.76837158203125e-7f;  // 2^-21: four ulp of slack either side
+    float a0 = (n.xy0.x - o.x) * id.x, b0 = (n.xy0.y - o.x) * id.x;
+    float a1 = (n.xy1.x - o.x) * id.x, b1 = (n.xy1.y - o.x) * id.x;
+    float tn0 = fmaxf(fminf(a0, b0), t_min), tf0 = fminf(fmaxf(a0, b0), t_max);
+    float tn1 = fmaxf(fminf(a1, b1), t_min), tf1 = fminf(fmaxf(a1, b1), t_max);
+    a0 = (n.xy0.z - o.y) * id.y; b0 = (n.xy0.w - o.y) * id.y;
+    a1 = (n.xy1.z - o.y) * id.y; b1 = (n.xy1.w - o.y) * id.y;
+    tn0 = fmaxf(fminf(a0, b0), tn0); tf0 = fminf(fmaxf(a0, b0), tf0);
+    tn1 = fmaxf(fminf(a1, b1), tn1); tf1 = fminf(fmaxf(a1, b1), tf1);
+    a0 = (n.z01.x - o.z) * id.z; b0 = (n.z01.y - o.z) * id.z;
+    a1 = (n.z01.z - o.z) * id.z; b1 = (n.z01.w - o.z) * id.z;
+    tn0 = fmaxf(fminf(a0, b0), tn0); tf0 = fminf(fmaxf(a0, b0), tf0);
+    tn1 = fmaxf(fminf(a1, b1), tn1); tf1 = fminf(fmaxf(a1, b1), tf1);
+    h0 = fmaf(-fabsf(tn0), kWiden, tn0) <= fmaf(fabsf(tf0), kWiden, tf0);
+    h1 = fmaf(-fabsf(tn1), kWiden, tn1) <= fmaf(fabsf(tf1), kWiden, tf1);
+    n0 = tn0;
+    n1 = tn1;
+}
+
+struct HitRec {
+    float t;
+    uint32_t prim;  // MRT_REF of the sphere / triangle / volume hit, kNone = miss
+    uint32_t inst;  // instance index the triangle was reached through, kNone otherwise
+};
+
+__device__ __forceinline__ Ray to_instance_space(const DInstance& in, const Ray& w) {  // geom.rs:405-408
+    if (in.flags & MRT_INSTANCE_IDENTITY) return w;                                   // Model::intersect :318-319: no transform
+    return Ray{xform(in.inv0, in.inv1, in.inv2, w.o, 1.0f), xform(in.inv0, in.inv1, in.inv2, w.d, 0.0f)};
+}
+
+// Volume::intersect geom.rs:612-655 for a sphere target. xi = the free-flight uniform (f32::rand(), :638).
+__device__ __forceinline__ bool volume_test(const DScene& sc, const mrt_volume& vol, const Ray& r, float t_min, float t_max, float xi, float& t_out) {
+    const float inf = __int_as_float(0x7f800000);
+    float4 s = __ldg(&sc.spheres[MRT_REF_INDEX(vol.target)]);
+    float enter, exit_;
+    if (!sphere_test(s, r, -inf, inf, enter)) return false;
+    if (!sphere_test(s, r, enter + 0.0001f, inf, exit_)) return false;
+    if (enter < t_min) enter = t_min;
+    if (exit_ > t_max) exit_ = t_max;
+    if (enter >= exit_) return false;
+    if (enter < 0.0f) enter = 0.0f;
+    float ray_length = length(r.d);
+    float inside = (exit_ - enter) * ray_length;
+    float hit_distance = logf(xi) * vol.neg_inv_density;
+    if (hit_distance > inside) return false;
+    t_out = enter + hit_distance / ray_length;
+    return true;
+}
+
+// Closest hit over World.objects (world.rs:131-144) through the flattened TLAS / BLAS.
+// Differences from BvhNode::intersect (geom.rs:186-200), none of which can change a closest hit except on exact-t
+// ties: iterative with an explicit per-thread stack, nearer child first, subtree skipped when its box lies beyond
+// the current closest t.
+template <bool COUNT>
+__device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, float t_min, float t_max, const RngKey& key, VisitCounters* cnt) {
+    uint32_t stack[kStackSize];
+    int sp = 0;
+    if (sc.n_roots <= 8) {
+        for (int i = (int)sc.n_roots - 1; i >= 0; --i) stack[sp++] = sc.roots[i];
+    } else {
+        // pre-BVH world with many objects: test them one by one (world.rs:135-140) without using the stack
+    }
+    HitRec best{t_max, kNone, kNone};
+    Ray r = world;
+    V3 id = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+    uint32_t cur_inst = kNone;
+    uint32_t linear_next = (sc.n_roots > 8) ? 0u : kNone;
+
+    for (;;) {
+        uint32_t ref;
+        if (sp > 0) ref = stack[--sp];
+        else if (linear_next != kNone && linear_next < sc.n_roots) ref = sc.roots_ext[linear_next++];
+        else break;
+
+        // descend through inner nodes
+        while (ref != kSentinel && MRT_REF_KIND(ref) == MRT_PRIM_NODE) {
+            const DNode* np = &sc.nodes[MRT_REF_INDEX(ref)];
+            DNode n;
+            n.xy0 = __ldg(&np->xy0);
+            n.xy1 = __ldg(&np->xy1);
+            n.z01 = __ldg(&np->z01);
+            uint4 ch = __ldg(reinterpret_cast<const uint4*>(&np->child0));
+            if (COUNT) cnt->node_visits++;
+            bool h0, h1;
+            float n0, n1;
+            slab2(n, r.o, id, t_min, best.t, h0, h1, n0, n1);
+            h0 = h0 && ch.x != kNone;
+            h1 = h1 && ch.y != kNone;
+            if (h0 && h1) {
+                bool swap = n1 < n0;
+                stack[sp++] = swap ? ch.x : ch.y;
+                ref = swap ? ch.y : ch.x;
+            } else if (h0) {
+                ref = ch.x;
+            } else if (h1) {
+                ref = ch.y;
+            } else {
+                ref = kNone;
+                break;
+            }
+        }
+        if (ref == kNone) continue;
+        if (ref == kSentinel) {  // leaving an instance: back to the world-space ray
+            r = world;
+            id = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+            cur_inst = kNone;
+            continue;
+        }
+        const uint32_t idx = MRT_REF_INDEX(ref);
+        switch (MRT_REF_KIND(ref)) {
+            case MRT_PRIM_TRIANGLE: {
+                if (COUNT) cnt->tri_tests++;
+                const DTriVerts* tp = &sc.tri_verts[idx];
+                DTriVerts tv;
+                tv.a = __ldg(&tp->a);
+                tv.b = __ldg(&tp->b);
+                tv.c = __ldg(&tp->c);
+                float t;
+                if (triangle_test(tv, r, t_min, best.t, t)) best = HitRec{t, ref, cur_inst};
+                break;
+            }
+            case MRT_PRIM_SPHERE: {
+                if (COUNT) cnt->sphere_tests++;
+                float t;
+                if (sphere_test(__ldg(&sc.spheres[idx]), r, t_min, best.t, t)) best = HitRec{t, ref, kNone};
+                break;
+            }
+            case MRT_PRIM_INSTANCE: {
+                if (COUNT) cnt->instance_tests++;
+                const DInstance* ip = &sc.instances[idx];
+                DInstance in;
+                in.inv0 = __ldg(&ip->inv0);
+                in.inv1 = __ldg(&ip->inv1);
+                in.inv2 = __ldg(&ip->inv2);
+                uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
+                in.flags = meta.z;
+                r = to_instance_space(in, world);
+                id = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+                cur_inst = idx;
+                stack[sp++] = kSentinel;
+                stack[sp++] = meta.x;  // BLAS root
+                break;
+            }
+            case MRT_PRIM_VOLUME: {
+                if (COUNT) cnt->volume_tests++;
+                mrt_volume vol = sc.volumes[idx];
+                Rand4 xi = draw4(key, kStreamVolume + idx);
+                float t;
+                if (volume_test(sc, vol, r, t_min, best.t, xi.x, t)) best = HitRec{t, ref, kNone};
+                break;
+            }
+            default: break;
+        }
+    }
+    if (best.prim == kNone) best.t = t_max;
+    return best;
+}
+
+// ---- surfaces (texture.rs) -------------------------------------------------------------------------------------
+struct V4 {
+    float x, y, z, w;
+};
+__device__ __forceinline__ V4 v4(float4 a) { return V4{a.x, a.y, a.z, a.w}; }
+__device__ __forceinline__ V4 operator*(V4 a, float s) { return V4{a.x * s, a.y * s, a.z * s, a.w * s}; }
+__device__ __forceinline__ V4 operator+(V4 a, V4 b) { return V4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+__device__ __forceinline__ V4 operator-(V4 a, V4 b) { return V4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+__device__ __forceinline__ float fractf_(float x) { return x - truncf(x); }
+__device__ __forceinline__ float wrap1(int mode, float x) {  // WrapMode::wrap texture.rs:277-300
+    if (mode == MRT_WRAP_REPEAT) {
+        x = (x < 0.0f) ? 1.0f - fractf_(fabsf(x)) : x;
+        x = (x > 1.0f) ? fractf_(x) : x;
+        return x;
+    }
+    return fmaxf(fminf(x, 1.0f), 0.0f);
+}
+__device__ __forceinline__ uint32_t as_index(float v, uint32_t limit) {  // Rust `as usize` saturates; the reference would panic past the edge
+    if (!(v > 0.0f)) return 0;
+    uint32_t i = (v >= 4294967040.0f) ? 0xFFFFFFFFu : (uint32_t)v;
+    return i < limit ? i : limit - 1;
+}
+__device__ __forceinline__ V4 texture_get(const DScene& sc, int tex, float u, float v) {  // Texture::get_f texture.rs:126-148
+    mrt_texture t = sc.textures[tex];
+    float x = wrap1(t.wrap, u) * (float)(t.width - 1);
+    float y = wrap1(t.wrap, v) * (float)(t.height - 1);
+    uint32_t x0 = as_index(floorf(x), t.width), x1 = as_index(ceilf(x), t.width);
+    uint32_t y0 = as_index(floorf(y), t.height), y1 = as_index(ceilf(y), t.height);
+    const float4* px = sc.texels + t.texel_offset;
+    float tx = x - (float)x0;
+    V4 p0 = v4(__ldg(&px[(size_t)y0 * t.width + x0])) * (1.0f - tx) + v4(__ldg(&px[(size_t)y0 * t.width + x1])) * tx;
+    V4 p1 = v4(__ldg(&px[(size_t)y1 * t.width + x0])) * (1.0f - tx) + v4(__ldg(&px[(size_t)y1 * t.width + x1])) * tx;
+    float ty = y - (float)y0;
+    return p1 * ty + p0 * (1.0f - ty);
+}
+__device__ __noinline__ V4 surface_get_slow(const DScene& sc, int surface, float u, float v);
+__device__ __forceinline__ V4 surface_get(const DScene& sc, int surface, float u, float v) {  // Surface::get_f
+    mrt_surface s = sc.surfaces[surface];
+    if (s.kind == MRT_SURF_SOLID) return V4{s.color[0], s.color[1], s.color[2], s.color[3]};  // texture.rs:191-193
+    if (s.kind == MRT_SURF_TEXTURE) return texture_get(sc, s.a, u, v);
+    return surface_get_slow(sc, surface, u, v);
+}
+__device__ __noinline__ V4 surface_get_slow(const DScene& sc, int surface, float u, float v) {
+    mrt_surface s = sc.surfaces[surface];
+    switch (s.kind) {
+        case MRT_SURF_YCBCR: {  // texture.rs:233-247 (BT.709 YCbCr -> RGB, clamp, powf 2.2)
+            const float KR = 0.2126f, KG = 0.7152f, KB = 0.0722f;
+            V4 l = texture_get(sc, s.a, u, v), c = texture_get(sc, s.b, u, v);
+            float Y = l.x, cb = c.x - 0.5f, cr = c.y - 0.5f;
+            float m11 = -(KB / KG) * (2.0f - 2.0f * KB), m12 = 2.0f - 2.0f * KB;
+            float m20 = 2.0f - 2.0f * KR, m21 = -(KR / KG) * (2.0f - 2.0f * KR);
+            float rr = ((1.0f * Y + 0.0f * cb) + m20 * cr) + 0.0f * 1.0f;
+            float gg = ((1.0f * Y + m11 * cb) + m21 * cr) + 0.0f * 1.0f;
+            float bb = ((1.0f * Y + m12 * cb) + 0.0f * cr) + 0.0f * 1.0f;
+            rr = powf(fmaxf(fminf(rr, 1.0f), 0.0f), 2.2f);
+            gg = powf(fmaxf(fminf(gg, 1.0f), 0.0f), 2.2f);
+            bb = powf(fmaxf(fminf(bb, 1.0f), 0.0f), 2.2f);
+            return V4{rr, gg, bb, 1.0f};
+        }
+        case MRT_SURF_BLEND: {  // texture.rs:250-334
+            V4 l = surface_get(sc, s.a, u, v), r = surface_get(sc, s.b, u, v);
+            switch (s.mode) {
+                case MRT_BLEND_LIGHTEN: return V4{fmaxf(l.x, r.x), fmaxf(l.y, r.y), fmaxf(l.z, r.z), fmaxf(l.w, r.w)};
+                case MRT_BLEND_DARKEN: return V4{fminf(l.x, r.x), fminf(l.y, r.y), fminf(l.z, r.z), fminf(l.w, r.w)};
+                case MRT_BLEND_ADDITION: { V4 a = l + r; return V4{fminf(a.x, 1.0f), fminf(a.y, 1.0f), fminf(a.z, 1.0f), fminf(a.w, 1.0f)}; }
+                default: { V4 a = l - r; return V4{fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f)}; }
+            }
+        }
+        case MRT_SURF_FALLBACK: {  // texture.rs:356-359
+            V4 c = surface_get(sc, s.a, u, v);
+            return (V4{s.color[0], s.color[1], s.color[2], s.color[3]} * (1.0f - c.w)) + (c * c.w);
+        }
+        default: return V4{0, 0, 0, 0};
+    }
+}
+
+// ---- closest-hit attributes (the part of Hit the reference fills for every candidate; here once) -----------------
+struct Surfel {
+    V3 point, normal;
+    float u, v;
+    bool has_uv, front_face;
+    int32_t material;
+    uint32_t object_id, tri_id;
+};
+__device__ __forceinline__ void set_face_normal(Surfel& s, const Ray& r, V3 outward) {  // geom.rs:17-24
+    s.front_face = dot(r.d, outward) < 0.0f;
+    s.normal = s.front_face ? outward : -outward;
+}
+// Material resolution N2: Triangle.material -> Model.material -> Instance.material (geom.rs:579, 321-323, 413-415)
+__device__ __forceinline__ int32_t hit_material(const DScene& sc, const HitRec& h) {
+    const uint32_t idx = MRT_REF_INDEX(h.prim);
+    switch (MRT_REF_KIND(h.prim)) {
+        case MRT_PRIM_SPHERE: return sc.sphere_aux[idx].material;
+        case MRT_PRIM_VOLUME: return sc.volumes[idx].material;
+        case MRT_PRIM_TRIANGLE: {
+            int32_t m = (h.inst != kNone) ? sc.instances[h.inst].material : -1;
+            return m >= 0 ? m : sc.tri_shading[idx].material;
+        }
+        default: return -1;
+    }
+}
+__device__ __forceinline__ Surfel resolve_hit(const DScene& sc, const Ray& world, const HitRec& h, int32_t material) {
+    Surfel s;
+    s.has_uv = false;
+    s.u = s.v = 0.0f;
+    s.material = material;
+    s.tri_id = kNone;
+    const uint32_t idx = MRT_REF_INDEX(h.prim);
+    switch (MRT_REF_KIND(h.prim)) {
+        case MRT_PRIM_SPHERE: {  // geom.rs:77-91
+            float4 sp = __ldg(&sc.spheres[idx]);
+            s.point = ray_at(world, h.t);
+            V3 n = (s.point - v3(sp)) / sp.w;
+            set_face_normal(s, world, n);
+            s.object_id = sc.sphere_aux[idx].object_id;
+            break;
+        }
+        case MRT_PRIM_VOLUME: {  // geom.rs:644-651
+            s.point = ray_at(world, h.t);
+            s.normal = V3{1.0f, 0.0f, 0.0f};
+            s.front_face = true;
+            s.object_id = sc.volumes[idx].object_id;
+            break;
+        }
+        default: {  // triangle, geom.rs:535-577, reached through Instance::intersect :404-420 or Model::intersect :318-328
+            const DInstance* ip = &sc.instances[h.inst];
+            DInstance in;
+            in.inv0 = __ldg(&ip->inv0); in.inv1 = __ldg(&ip->inv1); in.inv2 = __ldg(&ip->inv2);
+            in.fwd0 = __ldg(&ip->fwd0); in.fwd1 = __ldg(&ip->fwd1); in.fwd2 = __ldg(&ip->fwd2);
+            uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
+            in.flags = meta.z;
+            Ray r = to_instance_space(in, world);
+            const DTriVerts* tp = &sc.tri_verts[idx];
+            V3 va = v3(__ldg(&tp->a)), vb = v3(__ldg(&tp->b)), vc = v3(__ldg(&tp->c));
+            const mrt_tri_shading& sh = sc.tri_shading[idx];
+            V3 point = ray_at(r, h.t);
+            V3 d0 = va - point, d1 = vb - point, d2 = vc - point;
+            float area = length(cross(va - vb, va - vc));
+            float a0 = length(cross(d1, d2)) / area;
+            float a1 = length(cross(d2, d0)) / area;
+            float a2 = length(cross(d0, d1)) / area;
+            V3 na = v3(sh.normal[0], sh.normal[1], sh.normal[2]), nb = v3(sh.normal[3], sh.normal[4], sh.normal[5]), nc = v3(sh.normal[6], sh.normal[7], sh.normal[8]);
+            V3 normal = na * a0 + nb * a1 + nc * a2;
+            if (sh.flags & MRT_TRI_HAS_UV) {
+                s.has_uv = true;
+                s.u = (sh.uv[0] * a0 + sh.uv[2] * a1) + sh.uv[4] * a2;
+                s.v = (sh.uv[1] * a0 + sh.uv[3] * a1) + sh.uv[5] * a2;
+                // Material::normal is None for every material in material.rs (default :21-23): no tangent-space branch is reachable
+            }
+            set_face_normal(s, r, normal);
+            if (in.flags & MRT_INSTANCE_IDENTITY) {
+                s.point = point;
+            } else {  // geom.rs:411-412: forward matrix for both, normal re-normalised
+                s.point = xform(in.fwd0, in.fwd1, in.fwd2, point, 1.0f);
+                s.normal = unit(xform(in.fwd0, in.fwd1, in.fwd2, s.normal, 0.0f));
+            }
+            s.object_id = meta.w;
+            s.tri_id = idx - sc.blas[ip->pad[0]].first_tri;
+            break;
+        }
+    }
+    return s;
+}
+
+// ---- backgrounds (material.rs:39-190) ---------------------------------------------------------------------------
+__device__ __forceinline__ V3 background(const DScene& sc, const Ray& r) {
+    const mrt_background& bg = sc.bg;
+    switch (bg.kind) {
+        case MRT_BG_SKY: {  // :57-62
+            V3 ud = unit(r.d);
+            float t = 0.5f * (ud.y + 1.0f);
+            return (V3{1.0f, 1.0f, 1.0f} * (1.0f - t)) + (V3{0.5f, 0.7f, 1.0f} * t);
+        }
+        case MRT_BG_SKYSPHERE: {  // :75-88
+            const float PI = 3.14159265358979323846f;
+            V3 p = unit(r.d);
+            float theta = acosf(p.y);
+            float phi = atan2f(p.z * -1.0f, p.x) + PI;
+            V4 c = surface_get(sc, bg.surface[0], phi / (2.0f * PI), theta / PI);
+            return V3{c.x, c.y, c.z};
+        }
+        case MRT_BG_CUBEMAP: {  // :123-189
+            const float* m = bg.transform;
+            V3 d = r.d;
+            V3 p{((m[0] * d.x + m[4] * d.y) + m[8] * d.z) + m[12] * 0.0f, ((m[1] * d.x + m[5] * d.y) + m[9] * d.z) + m[13] * 0.0f,
+                 ((m[2] * d.x + m[6] * d.y) + m[10] * d.z) + m[14] * 0.0f};
+            V3 a{fabsf(p.x), fabsf(p.y), fabsf(p.z)};
+            bool xl = a.x >= a.y && a.x >= a.z, yl = a.y >= a.x && a.y >= a.z, zl = a.z >= a.x && a.z >= a.y;
+            int index = 0;
+            float max_axis = 0.0f, u = 0.0f, v = 0.0f;
+            if (xl) {
+                if (p.x > 0.0f) { index = 0; u = p.z * -1.0f; v = p.y; } else { index = 1; u = p.z; v = p.y; }
+                max_axis = a.x;
+            } else if (yl) {
+                if (p.y > 0.0f) { index = 3; u = p.x; v = p.z * -1.0f; } else { index = 2; u = p.x; v = p.z; }
+                max_axis = a.y;
+            } else if (zl) {
+                if (p.z > 0.0f) { index = 4; u = p.x; v = p.y; } else { index = 5; u = p.x * -1.0f; v = p.y; }
+                max_axis = a.z;
+            }
+            V4 c = surface_get(sc, bg.surface[index], 0.5f * (u / max_axis + 1.0f), 0.5f * (v / max_axis + 1.0f));
+            return V3{c.x, c.y, c.z};
+        }
+        default: return V3{bg.color[0], bg.color[1], bg.color[2]};
+    }
+}
+
+// ---- materials (material.rs) --------------------------------------------------------------------------------------
+__device__ __forceinline__ float reflectance(float cosine, float ref_idx) {  // :296-299
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    float x = 1.0f - cosine;
+    float x2 = x * x;
+    return r0 + (1.0f - r0) * (x2 * x2 * x);
+}
+struct ScatterOut {
+    bool scattered;
+    V3 attenuation, dir;
+    V3 emitted;
+};
+// Mix (material.rs:391-426): one independent coin per call and per nesting level, then the chosen child
+__device__ __forceinline__ mrt_material pick_material(const DScene& sc, int32_t m, const RngKey& key, uint32_t stream) {
+    mrt_material mat = sc.materials[m];
+    uint32_t level = 0;
+    while (mat.kind == MRT_MAT_MIX && level < 16) {
+        Rand4 c = draw4(key, stream + level);
+        mat = sc.materials[(c.x < mat.p[0]) ? mat.left : mat.right];
+        ++level;
+    }
+    return mat;
+}
+__device__ __forceinline__ V3 surface_rgb(const DScene& sc, int surface, const Surfel& s) {  // get_f(hit.uv.unwrap_or(0)).contract()
+    V4 c = surface_get(sc, surface, s.has_uv ? s.u : 0.0f, s.has_uv ? s.v : 0.0f);
+    return V3{c.x, c.y, c.z};
+}
+__device__ __forceinline__ void lambertian_scatter(const DScene& sc, const mrt_material& mat, const Surfel& s, float xa, float xb, ScatterOut& out) {  // :205-220
+    V3 dir = s.normal + sample_unit_vector(xa, xb);
+    if (near_zero(dir)) dir = s.normal;
+    out.scattered = true;
+    out.dir = dir;
+    out.attenuation = surface_rgb(sc, mat.surface, s);
+}
+// Hit::emit + Hit::scatter (geom.rs:26-32) for a resolved material kind (never MIX)
+__device__ __forceinline__ void scatter_kind(const DScene& sc, const mrt_material& mat, const Ray& ray, const Surfel& s, const Rand4& xi, ScatterOut& out) {
+    out.scattered = false;
+    switch (mat.kind) {
+        case MRT_MAT_LAMBERTIAN: lambertian_scatter(sc, mat, s, xi.x, xi.y, out); break;
+        case MRT_MAT_METAL: {  // :261-279
+            V3 reflected = reflect(unit(ray.d), s.normal);
+            V3 dir = reflected + (sample_unit_ball(xi.x, xi.y, xi.z) * mat.p[0]);
+            if (dot(dir, s.normal) > 0.0f) {
+                out.scattered = true;
+                out.dir = dir;
+                out.attenuation = surface_rgb(sc, mat.surface, s);
+            }
+            break;
+        }
+        case MRT_MAT_DIELECTRIC:
+        case MRT_MAT_SPECULAR: {  // :302-328, :352-378
+            float ratio = s.front_face ? 1.0f / mat.p[0] : mat.p[0];
+            V3 ud = unit(ray.d);
+            float cos_theta = fminf(dot(-ud, s.normal), 1.0f);
+            float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+            bool cannot_refract = ratio * sin_theta > 1.0f;
+            if (cannot_refract || reflectance(cos_theta, ratio) > xi.x) {
+                out.scattered = true;
+                out.dir = reflect(ud, s.normal);
+                out.attenuation = V3{1.0f, 1.0f, 1.0f};
+            } else if (mat.kind == MRT_MAT_DIELECTRIC) {
+                out.scattered = true;
+                out.dir = refract(ud, s.normal, ratio);
+                out.attenuation = V3{1.0f, 1.0f, 1.0f};
+            } else {
+                lambertian_scatter(sc, mat, s, xi.y, xi.z, out);  // Specular delegates to its inner Lambertian
+            }
+            break;
+        }
+        case MRT_MAT_ISOTROPIC:  // :439-444
+            out.scattered = true;
+            out.dir = sample_unit_ball(xi.x, xi.y, xi.z);
+            out.attenuation = V3{mat.p[0], mat.p[1], mat.p[2]};
+            break;
+        default: break;  // ABSORB (:385-389), DIFFUSE_LIGHT (:239-241): no scatter
+    }
+}
+
+}  // namespace mrt
