@@ -80,7 +80,8 @@ CUDA_API = {
 
 
 def scene_api(prefix, with_desc):
-    """Signatures of the scene-builder C surface; identical for libmrt_host.so (`mrth_`) and the test oracle (`orc_`)."""
+    """Signatures of the scene-builder C surface of libmrt_host.so (prefix `mrth`). The table is a function of the prefix so that
+    tests can bind a second implementation of the same surface (their CPU checker) and replay identical scenes into both."""
     p = prefix
     f3 = C.c_float * 3
     api = {

@@ -1292,7 +1292,7 @@ void orc_render_aov(orc_scene* s, uint32_t w, uint32_t h, uint64_t seed, int thr
             tl_cnt = &cnt;
             uint32_t y = row.fetch_add(1);
             while (y < h) {
-                Rng rng(splitmix(seed ^ (0xA0Full << 32) ^ y));  // per-row stream: output independent of thread count
+                Rng rng(splitmix(splitmix(seed ^ 0xA0F0A0F0ull) + y));  // per-row stream: output independent of thread count
                 tl_rng = &rng;
                 for (uint32_t x = 0; x < w; ++x) {
                     F u = (F)x / (F)(w - 1);  // main.rs:189-190 (no jitter)
@@ -1343,7 +1343,7 @@ void orc_render(orc_scene* s, uint32_t w, uint32_t h, uint32_t spp, uint32_t max
             for (;;) {
                 uint32_t frame = next_frame.fetch_add(1);
                 if (frame >= spp) break;
-                Rng rng(splitmix(seed ^ (0xF4A3Eull << 32) ^ frame));  // per-frame stream: output independent of thread count
+                Rng rng(splitmix(splitmix(seed) + frame));  // per-frame stream: output independent of thread count
                 tl_rng = &rng;
                 for (uint32_t y = 0; y < h; ++y) {
                     for (uint32_t x = 0; x < w; ++x) {
