@@ -257,7 +257,14 @@ int mrt_accum_download(mrt_context* ctx, float* sum_rgb, uint32_t* sum_bounces, 
 int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8_t* out_rgb);
 
 /* knobs and counters (the reference only prints whole seconds, main.rs:270) */
-enum { MRT_OPT_COUNT_VISITS = 1, MRT_OPT_TIME_KERNELS = 2, MRT_OPT_POOL_SLOTS = 3 };
+enum {
+    MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */
+    MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
+    MRT_OPT_POOL_SLOTS = 3,   /* path-state slots (0 = default 2^22) */
+    MRT_OPT_REFILL_LANES = 4, /* k_extend: refill finished lanes when at least this many of a warp's 32 are idle */
+    MRT_OPT_NODE_LANES = 5,   /* k_extend: run a node-visit phase when at least this many lanes are at an inner node; 0 = no voting (chain mode) */
+    MRT_OPT_NODE_BURST = 6    /* k_extend: node visits per lane per node phase */
+};
 int mrt_set_option(mrt_context* ctx, int option, uint64_t value);
 int mrt_get_stats(mrt_context* ctx, mrt_stats* out);
 int mrt_synchronize(mrt_context* ctx);

@@ -47,13 +47,19 @@ struct QueueState {
 struct RenderParams {
     uint32_t w, h, npix, spp_begin, max_depth;
     uint2 seed;
+    uint32_t refill_lanes, node_lanes, node_burst;  // warp-vote thresholds of k_extend
 };
 
+// One path = one 64-byte slot = two 32-byte sectors: extend reads sector 0 and writes `hit`; shade reads both and rewrites
+// sector 0 and `thr`. Slots are reached through permuted index queues, so every 32-byte sector fetched is fully used.
+struct __align__(16) Slot {
+    float4 o;    // ray origin.xyz, pixel (as bits)
+    float4 d;    // ray direction.xyz, sample index (as bits)
+    uint4 hit;   // t (as bits), prim ref, instance, material
+    float4 thr;  // throughput.rgb, bounce (as bits)
+};
 struct Pool {
-    float4* ray_o;   // origin.xyz, pixel
-    float4* ray_d;   // direction.xyz, sample
-    float4* thr;     // throughput.rgb, bounce
-    uint4* hit;      // t, prim ref, instance, material
+    Slot* slot;
     uint32_t* q_ext[2];
     uint32_t* q_shade;  // Q_COUNT queues of `slots` entries
     uint32_t* free_list;
@@ -135,51 +141,111 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
         uint32_t pixel = (uint32_t)(wk % rp.npix);
         uint32_t sample = rp.spp_begin + (uint32_t)(wk / rp.npix);
         Ray r = camera_ray(cam, rp, pixel, sample, true);
-        pool.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
-        pool.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(sample));
-        pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+        Slot* sl = &pool.slot[slot];
+        sl->o = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
+        sl->d = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(sample));
+        sl->thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
         pool.q_ext[cur][n_cont + i] = slot;
     }
 }
+
+// Persistent lanes. Every thread keeps one traversal in flight; when at least `refill_lanes` lanes of a warp have finished, the
+// warp commits their hits (hit record + material-sorted shade queue, one atomic per warp and kind) and refills those lanes from
+// the ray queue with one atomic. Between refills each lane descends to its next leaf and tests it ("chain mode", node_lanes = 0).
+// A second scheduling mode (node_lanes > 0) makes the warp vote each iteration and run either one node visit or the pending
+// primitive tests with all lanes that want that kind of work; it raises the active lanes per instruction (8 -> 15 of 32 on the
+// Cornell box) but its per-iteration voting overhead cancels the gain on B200 (profiles/README.md), so chain mode is the default.
+constexpr uint32_t kRefillLanes = 24;  // defaults; MRT_OPT_REFILL_LANES / MRT_OPT_NODE_LANES / MRT_OPT_NODE_BURST override them
+constexpr uint32_t kNodeLanes = 0;
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
                                                 QueueState* q, int cur) {
     const uint32_t n = q->n_ext;
     const uint32_t* __restrict__ queue = pool.q_ext[cur];
-    VisitCounters cnt{0, 0, 0, 0, 0};
     const float inf = __int_as_float(0x7f800000);
+    const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    VisitCounters cnt{0, 0, 0, 0, 0};
+    uint32_t stack[kStackSize];
+    Traversal T;
+    T.sp = 0;
+    T.inst_base = 0;
+    T.linear_next = 0;
+    T.ref = kNone;
+    T.best = HitRec{inf, kNone, kNone};
+    RngKey key{0u, 0u, 0u, rp.seed};
+    uint32_t slot = 0;
+    bool active = false, pending = false, drained = false;
     for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(&q->ext_cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane_id();
-        const bool valid = i < n;
-        uint32_t slot = 0, kind = 0xFFu;
-        if (valid) {
-            slot = queue[i];
-            float4 o = pool.ray_o[slot], d = pool.ray_d[slot];
-            Ray r{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}};
-            RngKey key{__float_as_uint(o.w), __float_as_uint(d.w), 0u, rp.seed};
-            if (sc.n_volumes) key.bounce = __float_as_uint(pool.thr[slot].w);
-            HitRec h = traverse<COUNT>(sc, r, 0.001f, inf, key, &cnt);  // world.rs:68: [0.001, +inf)
-            int32_t m = -1;
-            kind = Q_MISS;
-            if (h.prim != kNone) {
-                m = hit_material(sc, h);
-                kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu || (!drained && (uint32_t)__popc(idle) >= rp.refill_lanes)) {
+            // ---- commit finished rays: world.rs:68 result -> hit record, shade queue by material kind -----------
+            uint32_t kind = 0xFFu;
+            if (pending) {
+                HitRec h = T.best;
+                if (h.prim == kNone) h.t = inf;
+                int32_t m = -1;
+                kind = Q_MISS;
+                if (h.prim != kNone) {
+                    m = hit_material(sc, h);
+                    kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
+                }
+                pool.slot[slot].hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
             }
-            pool.hit[slot] = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
+            const uint32_t peers = __match_any_sync(0xffffffffu, kind);
+            if (pending) {
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t qbase = 0;
+                if (lane == leader) qbase = atomicAdd(&q->n_shade[kind], __popc(peers));
+                qbase = __shfl_sync(peers, qbase, leader);
+                pool.q_shade[(size_t)kind * pool.slots + qbase + __popc(peers & lt_mask)] = slot;
+                pending = false;
+            }
+            // ---- refill idle lanes --------------------------------------------------------------------------------
+            if (!drained) {
+                const uint32_t want = __popc(idle);
+                const uint32_t leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&q->ext_cursor, want);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t i = base + __popc(idle & lt_mask);
+                if (!active && i < n) {
+                    slot = queue[i];
+                    const Slot* sl = &pool.slot[slot];
+                    float4 o = sl->o, d = sl->d;
+                    key.pixel = __float_as_uint(o.w);
+                    key.sample = __float_as_uint(d.w);
+                    if (sc.n_volumes) key.bounce = __float_as_uint(sl->thr.w);
+                    trav_begin(sc, T, stack, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, inf);  // world.rs:68: [0.001, +inf)
+                    active = true;
+                }
+                drained = base + want >= n;
+            }
+            if (__ballot_sync(0xffffffffu, active) == 0) break;
         }
-        // material-sorted shading queues: one atomic per (warp, kind)
-        uint32_t peers = __match_any_sync(0xffffffffu, kind);
-        if (valid) {
-            uint32_t leader = __ffs(peers) - 1;
-            uint32_t qbase = 0;
-            if (lane_id() == leader) qbase = atomicAdd(&q->n_shade[kind], __popc(peers));
-            qbase = __shfl_sync(peers, qbase, leader);
-            pool.q_shade[(size_t)kind * pool.slots + qbase + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
+        if (active && T.ref == kNone && !trav_pop(sc, T, stack)) {
+            active = false;
+            pending = true;
+        }
+        if (rp.node_lanes == 0) {  // chain mode: each lane descends to its next leaf and tests it before the warp votes again
+            if (active) {
+                while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
+                if (T.ref != kNone) trav_leaf<COUNT>(sc, T, stack, 0.001f, key, &cnt);
+            }
+            continue;
+        }
+        const bool at_node = active && ref_is_node(T.ref);
+        const bool at_leaf = active && !at_node;
+        const uint32_t nodes = __ballot_sync(0xffffffffu, at_node);
+        const uint32_t leaves = __ballot_sync(0xffffffffu, at_leaf);
+        if ((uint32_t)__popc(nodes) >= rp.node_lanes || leaves == 0) {
+            if (at_node) {
+                trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
+                for (uint32_t b = 1; b < rp.node_burst && ref_is_node(T.ref); ++b) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
+            }
+        } else {
+            if (at_leaf) trav_leaf<COUNT>(sc, T, stack, 0.001f, key, &cnt);
         }
     }
     if (COUNT) {
@@ -189,7 +255,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene s
         for (int k = 0; k < 5; ++k) {
             unsigned long long x = v[k];
             for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-            if (lane_id() == 0 && x) atomicAdd(&dst[k], x);
+            if (lane == 0 && x) atomicAdd(&dst[k], x);
         }
     }
 }
@@ -198,7 +264,8 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene s
 // radiance += throughput * emitted; throughput *= attenuation.
 __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams& rp, const Pool& pool, long long* accum, uint32_t* nonfinite,
                                             uint32_t kind, uint32_t slot, bool& cont) {
-    float4 o = pool.ray_o[slot], d = pool.ray_d[slot], th = pool.thr[slot];
+    Slot* sl = &pool.slot[slot];
+    float4 o = sl->o, d = sl->d, th = sl->thr;
     const uint32_t pixel = __float_as_uint(o.w), sample = __float_as_uint(d.w);
     uint32_t bounce = __float_as_uint(th.w);
     Ray ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}};
@@ -207,7 +274,7 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
     if (kind == Q_MISS) {  // world.rs:77
         accumulate(accum, nonfinite, pixel, thr * background(sc, ray));
     } else {
-        uint4 hr = pool.hit[slot];
+        uint4 hr = sl->hit;
         HitRec h{__uint_as_float(hr.x), hr.y, hr.z};
         RngKey key{pixel, sample, bounce, rp.seed};
         mrt_material mat = sc.materials[(int32_t)hr.w];
@@ -225,9 +292,9 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
             bounce += 1;
             if (bounce < rp.max_depth) {  // world.rs:66: the next call would be depth == 0 -> contributes 0
                 cont = true;
-                pool.ray_o[slot] = make_float4(s.point.x, s.point.y, s.point.z, o.w);
-                pool.ray_d[slot] = make_float4(sco.dir.x, sco.dir.y, sco.dir.z, d.w);
-                pool.thr[slot] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(bounce));
+                sl->o = make_float4(s.point.x, s.point.y, s.point.z, o.w);
+                sl->d = make_float4(sco.dir.x, sco.dir.y, sco.dir.z, d.w);
+                sl->thr = make_float4(thr.x, thr.y, thr.z, __uint_as_float(bounce));
             }
         }
     }
@@ -235,7 +302,7 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
         atomicAdd(reinterpret_cast<unsigned long long*>(&accum[(size_t)pixel * 4 + 3]), (unsigned long long)bounce);
 }
 
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
+__global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
                                                QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
     uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
     for (uint32_t kind = 0; kind < Q_COUNT; ++kind) {
@@ -392,6 +459,7 @@ struct mrt_context {
     // options
     bool opt_count = false, opt_time = false;
     uint64_t opt_pool_slots = 0;
+    uint32_t opt_refill_lanes = kRefillLanes, opt_node_lanes = kNodeLanes, opt_node_burst = 1;
     mrt_stats stats{};
     int grid_extend = 0, grid_extend_count = 0, grid_shade = 0, grid_generate = 0;
 };
@@ -433,7 +501,7 @@ static void free_scene(mrt_context* ctx) {
 }
 static void free_pool(mrt_context* ctx) {
     Pool& p = ctx->pool;
-    cudaFree(p.ray_o); cudaFree(p.ray_d); cudaFree(p.thr); cudaFree(p.hit);
+    cudaFree(p.slot);
     cudaFree(p.q_ext[0]); cudaFree(p.q_ext[1]); cudaFree(p.q_shade); cudaFree(p.free_list);
     p = Pool{};
 }
@@ -780,7 +848,7 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
-    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))};
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst};
     k_aov<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     AOV_TRY(cudaGetLastError());
     if (albedo) AOV_TRY(cudaMemcpyAsync(albedo, d_alb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
@@ -820,10 +888,7 @@ static int ensure_pool(mrt_context* ctx, uint64_t total_work) {
     cudaStreamSynchronize(ctx->stream);
     free_pool(ctx);
     Pool& p = ctx->pool;
-    MRT_CUDA(cudaMalloc(&p.ray_o, want * 16));
-    MRT_CUDA(cudaMalloc(&p.ray_d, want * 16));
-    MRT_CUDA(cudaMalloc(&p.thr, want * 16));
-    MRT_CUDA(cudaMalloc(&p.hit, want * 16));
+    MRT_CUDA(cudaMalloc(&p.slot, want * sizeof(Slot)));
     MRT_CUDA(cudaMalloc(&p.q_ext[0], want * 4));
     MRT_CUDA(cudaMalloc(&p.q_ext[1], want * 4));
     MRT_CUDA(cudaMalloc(&p.q_shade, want * 4 * Q_COUNT));
@@ -850,7 +915,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     if ((rc = ensure_pool(ctx, total))) return rc;
     st.pool_slots = ctx->pool.slots;
     Pool pool = ctx->pool;
-    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))};
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst};
 
     QueueState init;
     std::memset(&init, 0, sizeof init);
@@ -994,6 +1059,18 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
         case MRT_OPT_POOL_SLOTS:
             if (value != 0 && (value < 1024 || value > (1ull << 28))) return fail(ctx, MRT_E_INVALID, "pool slots out of range [1024, 2^28]");
             ctx->opt_pool_slots = value / 1024 * 1024;
+            return MRT_OK;
+        case MRT_OPT_REFILL_LANES:
+            if (value < 1 || value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [1, 32]");
+            ctx->opt_refill_lanes = (uint32_t)value;
+            return MRT_OK;
+        case MRT_OPT_NODE_BURST:
+            if (value < 1 || value > 64) return fail(ctx, MRT_E_INVALID, "burst out of range [1, 64]");
+            ctx->opt_node_burst = (uint32_t)value;
+            return MRT_OK;
+        case MRT_OPT_NODE_LANES:
+            if (value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [0, 32]");
+            ctx->opt_node_lanes = (uint32_t)value;
             return MRT_OK;
         default: return fail(ctx, MRT_E_INVALID, "unknown option");
     }

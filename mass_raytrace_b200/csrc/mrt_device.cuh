@@ -15,7 +15,6 @@
 namespace mrt {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr uint32_t kSentinel = 0xFFFFFFFEu;  // stack marker: leave the current instance, restore the world ray
 constexpr int kStackSize = 64;
 
 // ---- device scene (HBM layout; all arrays 16-byte aligned, fetched with 128-bit loads) -----------------------
@@ -244,113 +243,166 @@ __device__ __forceinline__ bool volume_test(const DScene& sc, const mrt_volume& 
     return true;
 }
 
-// Closest hit over World.objects (world.rs:131-144) through the flattened TLAS / BLAS.
-// Differences from BvhNode::intersect (geom.rs:186-200), none of which can change a closest hit except on exact-t
-// ties: iterative with an explicit per-thread stack, nearer child first, subtree skipped when its box lies beyond
-// the current closest t.
+// 1/x for the slab test only: one MUFU.RCP (<= 1 ulp, subnormals handled, 1/+-0 = +-inf). The slab test is widened by 4 ulp, which
+// covers this error; nothing that reaches a hit record uses it.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ V3 inv_dir(V3 d) { return V3{rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z)}; }
+
+// Closest hit over World.objects (world.rs:131-144) through the flattened TLAS / BLAS, as a resumable state machine whose
+// three kinds of work are separate functions, so that a warp can run each kind with as many lanes as possible (k_extend):
+//   trav_pop   next stack entry (leaving an instance restores the world ray)       -> T.ref = node | leaf, or finished
+//   trav_node  ONE inner-node visit: fetch 64 B, slab-test both children            -> T.ref = nearer child | none
+//   trav_leaf  one primitive: triangle / sphere / volume test, or instance entry    -> T.ref = none | BLAS root
+// Differences from BvhNode::intersect (geom.rs:186-200), none of which can change a closest hit except on exact-t ties:
+// iterative with an explicit per-thread stack, nearer child first, subtree skipped when its box lies beyond the current closest t.
+struct Traversal {
+    Ray r;              // ray in the current space (world, or the entered instance's)
+    V3 id;              // reciprocal direction for the slab test
+    Ray w;              // the world-space ray and its reciprocal direction (restored when an instance is left)
+    V3 wid;
+    HitRec best;        // best.t doubles as the shrinking t_max (world.rs:133, geom.rs:192)
+    uint32_t cur_inst;
+    uint32_t ref;          // what this lane does next: a node ref, a leaf ref, or kNone = pop
+    uint32_t linear_next;  // next entry of a > 8-object pre-BVH world list (world.rs:135-140), else n_roots
+    int sp;
+    int inst_base;         // stack height when the current instance was entered (0 in world space)
+};
+__device__ __forceinline__ bool ref_is_node(uint32_t ref) { return ref < (1u << 29); }  // kind 0 in the top three bits
+
+__device__ __forceinline__ void trav_begin(const DScene& sc, Traversal& T, uint32_t* stack, const Ray& world, float t_max) {
+    T.sp = 0;
+    T.linear_next = sc.n_roots;
+    if (sc.n_roots <= 8) {
+        for (int i = (int)sc.n_roots - 1; i >= 0; --i) stack[T.sp++] = sc.roots[i];
+    } else {
+        T.linear_next = 0;
+    }
+    T.best = HitRec{t_max, kNone, kNone};
+    T.w = world;
+    T.wid = inv_dir(world.d);
+    T.r = T.w;
+    T.id = T.wid;
+    T.cur_inst = kNone;
+    T.ref = kNone;
+    T.inst_base = 0;
+}
+
+// false when the traversal is complete (T.best is final). Entries pushed before an instance was entered sit below
+// T.inst_base: popping one of them means the BLAS is exhausted, i.e. Instance::intersect has returned (geom.rs:404-420).
+__device__ __forceinline__ bool trav_pop(const DScene& sc, Traversal& T, const uint32_t* stack) {
+    if (T.sp > 0) {
+        T.ref = stack[--T.sp];
+        if (T.sp < T.inst_base) {
+            T.r = T.w;
+            T.id = T.wid;
+            T.cur_inst = kNone;
+            T.inst_base = 0;
+        }
+        return true;
+    }
+    if (T.linear_next < sc.n_roots) {  // pre-BVH world list with more than 8 objects
+        T.ref = sc.roots_ext[T.linear_next++];
+        T.r = T.w;
+        T.id = T.wid;
+        T.cur_inst = kNone;
+        T.inst_base = 0;
+        return true;
+    }
+    return false;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trav_node(const DScene& sc, Traversal& T, uint32_t* stack, float t_min, VisitCounters* cnt) {
+    const DNode* np = &sc.nodes[MRT_REF_INDEX(T.ref)];
+    DNode n;
+    n.xy0 = __ldg(&np->xy0);
+    n.xy1 = __ldg(&np->xy1);
+    n.z01 = __ldg(&np->z01);
+    uint4 ch = __ldg(reinterpret_cast<const uint4*>(&np->child0));
+    if (COUNT) cnt->node_visits++;
+    bool h0, h1;
+    float n0, n1;
+    slab2(n, T.r.o, T.id, t_min, T.best.t, h0, h1, n0, n1);
+    h0 = h0 && ch.x != kNone;
+    h1 = h1 && ch.y != kNone;
+    if (h0 && h1) {
+        bool swap = n1 < n0;
+        stack[T.sp++] = swap ? ch.x : ch.y;
+        T.ref = swap ? ch.y : ch.x;
+    } else {
+        T.ref = h0 ? ch.x : (h1 ? ch.y : kNone);
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32_t* stack, float t_min, const RngKey& key, VisitCounters* cnt) {
+    const uint32_t ref = T.ref;
+    const uint32_t idx = MRT_REF_INDEX(ref);
+    T.ref = kNone;
+    switch (MRT_REF_KIND(ref)) {
+        case MRT_PRIM_TRIANGLE: {
+            if (COUNT) cnt->tri_tests++;
+            const DTriVerts* tp = &sc.tri_verts[idx];
+            DTriVerts tv;
+            tv.a = __ldg(&tp->a);
+            tv.b = __ldg(&tp->b);
+            tv.c = __ldg(&tp->c);
+            float t;
+            if (triangle_test(tv, T.r, t_min, T.best.t, t)) T.best = HitRec{t, ref, T.cur_inst};
+            break;
+        }
+        case MRT_PRIM_SPHERE: {
+            if (COUNT) cnt->sphere_tests++;
+            float t;
+            if (sphere_test(__ldg(&sc.spheres[idx]), T.r, t_min, T.best.t, t)) T.best = HitRec{t, ref, kNone};
+            break;
+        }
+        case MRT_PRIM_INSTANCE: {
+            if (COUNT) cnt->instance_tests++;
+            const DInstance* ip = &sc.instances[idx];
+            DInstance in;
+            in.inv0 = __ldg(&ip->inv0);
+            in.inv1 = __ldg(&ip->inv1);
+            in.inv2 = __ldg(&ip->inv2);
+            uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
+            in.flags = meta.z;
+            T.r = to_instance_space(in, T.w);  // only reachable from world space (no nested instances, geom.rs:336)
+            T.id = inv_dir(T.r.d);
+            T.cur_inst = idx;
+            T.inst_base = T.sp;
+            T.ref = meta.x;  // BLAS root: a node
+            break;
+        }
+        case MRT_PRIM_VOLUME: {
+            if (COUNT) cnt->volume_tests++;
+            mrt_volume vol = sc.volumes[idx];
+            Rand4 xi = draw4(key, kStreamVolume + idx);
+            float t;
+            if (volume_test(sc, vol, T.r, t_min, T.best.t, xi.x, t)) T.best = HitRec{t, ref, kNone};
+            break;
+        }
+        default: break;
+    }
+}
+
+// run a traversal to completion (AOV pass)
 template <bool COUNT>
 __device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, float t_min, float t_max, const RngKey& key, VisitCounters* cnt) {
     uint32_t stack[kStackSize];
-    int sp = 0;
-    if (sc.n_roots <= 8) {
-        for (int i = (int)sc.n_roots - 1; i >= 0; --i) stack[sp++] = sc.roots[i];
-    } else {
-        // pre-BVH world with many objects: test them one by one (world.rs:135-140) without using the stack
-    }
-    HitRec best{t_max, kNone, kNone};
-    Ray r = world;
-    V3 id = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
-    uint32_t cur_inst = kNone;
-    uint32_t linear_next = (sc.n_roots > 8) ? 0u : kNone;
-
-    for (;;) {
-        uint32_t ref;
-        if (sp > 0) ref = stack[--sp];
-        else if (linear_next != kNone && linear_next < sc.n_roots) ref = sc.roots_ext[linear_next++];
-        else break;
-
-        // descend through inner nodes
-        while (ref != kSentinel && MRT_REF_KIND(ref) == MRT_PRIM_NODE) {
-            const DNode* np = &sc.nodes[MRT_REF_INDEX(ref)];
-            DNode n;
-            n.xy0 = __ldg(&np->xy0);
-            n.xy1 = __ldg(&np->xy1);
-            n.z01 = __ldg(&np->z01);
-            uint4 ch = __ldg(reinterpret_cast<const uint4*>(&np->child0));
-            if (COUNT) cnt->node_visits++;
-            bool h0, h1;
-            float n0, n1;
-            slab2(n, r.o, id, t_min, best.t, h0, h1, n0, n1);
-            h0 = h0 && ch.x != kNone;
-            h1 = h1 && ch.y != kNone;
-            if (h0 && h1) {
-                bool swap = n1 < n0;
-                stack[sp++] = swap ? ch.x : ch.y;
-                ref = swap ? ch.y : ch.x;
-            } else if (h0) {
-                ref = ch.x;
-            } else if (h1) {
-                ref = ch.y;
-            } else {
-                ref = kNone;
-                break;
-            }
-        }
-        if (ref == kNone) continue;
-        if (ref == kSentinel) {  // leaving an instance: back to the world-space ray
-            r = world;
-            id = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
-            cur_inst = kNone;
-            continue;
-        }
-        const uint32_t idx = MRT_REF_INDEX(ref);
-        switch (MRT_REF_KIND(ref)) {
-            case MRT_PRIM_TRIANGLE: {
-                if (COUNT) cnt->tri_tests++;
-                const DTriVerts* tp = &sc.tri_verts[idx];
-                DTriVerts tv;
-                tv.a = __ldg(&tp->a);
-                tv.b = __ldg(&tp->b);
-                tv.c = __ldg(&tp->c);
-                float t;
-                if (triangle_test(tv, r, t_min, best.t, t)) best = HitRec{t, ref, cur_inst};
-                break;
-            }
-            case MRT_PRIM_SPHERE: {
-                if (COUNT) cnt->sphere_tests++;
-                float t;
-                if (sphere_test(__ldg(&sc.spheres[idx]), r, t_min, best.t, t)) best = HitRec{t, ref, kNone};
-                break;
-            }
-            case MRT_PRIM_INSTANCE: {
-                if (COUNT) cnt->instance_tests++;
-                const DInstance* ip = &sc.instances[idx];
-                DInstance in;
-                in.inv0 = __ldg(&ip->inv0);
-                in.inv1 = __ldg(&ip->inv1);
-                in.inv2 = __ldg(&ip->inv2);
-                uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
-                in.flags = meta.z;
-                r = to_instance_space(in, world);
-                id = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
-                cur_inst = idx;
-                stack[sp++] = kSentinel;
-                stack[sp++] = meta.x;  // BLAS root
-                break;
-            }
-            case MRT_PRIM_VOLUME: {
-                if (COUNT) cnt->volume_tests++;
-                mrt_volume vol = sc.volumes[idx];
-                Rand4 xi = draw4(key, kStreamVolume + idx);
-                float t;
-                if (volume_test(sc, vol, r, t_min, best.t, xi.x, t)) best = HitRec{t, ref, kNone};
-                break;
-            }
-            default: break;
+    Traversal T;
+    trav_begin(sc, T, stack, world, t_max);
+    while (trav_pop(sc, T, stack)) {
+        while (T.ref != kNone) {
+            if (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, t_min, cnt);
+            else trav_leaf<COUNT>(sc, T, stack, t_min, key, cnt);
         }
     }
-    if (best.prim == kNone) best.t = t_max;
-    return best;
+    if (T.best.prim == kNone) T.best.t = t_max;
+    return T.best;
 }
 
 // ---- surfaces (texture.rs) -------------------------------------------------------------------------------------
