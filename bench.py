@@ -201,6 +201,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line even under NCCL_DEBUG=VERSION/INFO
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, w, h, spp_default, desc = WORKLOADS[args.workload]

@@ -465,8 +465,12 @@ class Renderer:
         if rc != 0:
             raise MrtError(f"{what} = {rc}: {self.lib.mrt_last_error(self._h).decode()}")
 
-    def set_scene(self, scene: NativeScene):
-        self._check(self.lib.mrt_scene_upload(self._h, scene.desc()), "mrt_scene_upload")
+    def set_scene(self, scene: NativeScene, keep_topology=False):
+        """mrt_scene_upload (+ mrt_camera_set). keep_topology: traverse the caller's BVH as built by BvhNode::new (geom.rs:109-161)
+        instead of the library's SAH rebuild (MRT_SCENE_KEEP_TOPOLOGY); results are the same except on exact-t ties."""
+        desc = scene.desc()
+        desc.contents.flags = 1 if keep_topology else 0
+        self._check(self.lib.mrt_scene_upload(self._h, desc), "mrt_scene_upload")
         if scene.has_camera:
             self._check(self.lib.mrt_camera_set(self._h, scene.camera_struct()), "mrt_camera_set")
 

@@ -18,10 +18,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
 #include "mrt.h"
+#include "mrt_bvh_build.h"
 #include "mrt_debug.h"
 #include "mrt_device.cuh"
 
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
 constexpr uint32_t kRefillLanes = 24;  // defaults; MRT_OPT_REFILL_LANES / MRT_OPT_NODE_LANES / MRT_OPT_NODE_BURST override them
 constexpr uint32_t kNodeLanes = 0;
 
-template <bool COUNT>
+template <bool COUNT, bool ALPHA>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
                                                 QueueState* q, int cur) {
     const uint32_t n = q->n_ext;
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene s
         if (rp.node_lanes == 0) {  // chain mode: each lane descends to its next leaf and tests it before the warp votes again
             if (active) {
                 while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
-                if (T.ref != kNone) trav_leaf<COUNT>(sc, T, stack, 0.001f, key, &cnt);
+                if (T.ref != kNone) trav_leaf<COUNT, ALPHA>(sc, T, stack, 0.001f, key, &cnt);
             }
             continue;
         }
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene s
                 for (uint32_t b = 1; b < rp.node_burst && ref_is_node(T.ref); ++b) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
             }
         } else {
-            if (at_leaf) trav_leaf<COUNT>(sc, T, stack, 0.001f, key, &cnt);
+            if (at_leaf) trav_leaf<COUNT, ALPHA>(sc, T, stack, 0.001f, key, &cnt);
         }
     }
     if (COUNT) {
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ DScene
 }
 
 // PASS A (main.rs:166-222): Camera::albedo_normal (world.rs:81-93) at pixel centres
+template <bool ALPHA>
 __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp,
                                              float* albedo, float* normal, uint32_t* object_id, uint32_t* tri_id, float* t_out) {
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, 
     const float inf = __int_as_float(0x7f800000);
     Ray ray = camera_ray(cam, rp, pixel, 0u, false);
     RngKey key{pixel, 0u, 0u, rp.seed};
-    HitRec h = traverse<false>(sc, ray, 0.001f, inf, key, nullptr);
+    HitRec h = traverse<false, ALPHA>(sc, ray, 0.001f, inf, key, nullptr);
     V3 a, n{0.0f, 0.0f, 0.0f};
     uint32_t obj = kNone, tri = kNone;
     float t = inf;
@@ -461,7 +464,7 @@ struct mrt_context {
     uint64_t opt_pool_slots = 0;
     uint32_t opt_refill_lanes = kRefillLanes, opt_node_lanes = kNodeLanes, opt_node_burst = 1;
     mrt_stats stats{};
-    int grid_extend = 0, grid_extend_count = 0, grid_shade = 0, grid_generate = 0;
+    int grid_extend = 0, grid_extend_count = 0, grid_extend_slow = 0, grid_shade = 0, grid_generate = 0;
 };
 
 static std::string g_create_error;
@@ -560,10 +563,12 @@ int mrt_context_create(int device, void* stream, mrt_context** out) {
     if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return bail("cudaEventCreate", e);
     // persistent grids: SM count x resident blocks per SM
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false>, 128, 0);
     ctx->grid_extend = ctx->n_sms * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, false>, 128, 0);
     ctx->grid_extend_count = ctx->n_sms * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, true>, 128, 0);
+    ctx->grid_extend_slow = ctx->n_sms * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
     ctx->grid_shade = ctx->n_sms * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_generate, 256, 0);
@@ -732,25 +737,144 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if (tlas_depth + blas_depth + 2 + (int)std::min<uint32_t>(s->n_roots, 8) > kStackSize)
         return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack");
 
-    // ---- re-layout and copy ----------------------------------------------------------------------------------
+    // ---- acceleration structure: the caller's topology re-laid out, or (default) a SAH rebuild -----------------------------
+    if (s->n_tris > kTriIndexMask) return fail(ctx, MRT_E_UNSUPPORTED, "more than 2^27 triangles");
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     DScene d{};
-    std::vector<DNode> nodes(s->n_nodes);
+    const bool keep = (s->flags & MRT_SCENE_KEEP_TOPOLOGY) != 0;
     const float inf = INFINITY;
-    for (uint64_t i = 0; i < s->n_nodes; ++i) {
-        const mrt_node& n = s->nodes[i];
-        float l0[3], h0[3], l1[3] = {inf, inf, inf}, h1[3] = {-inf, -inf, -inf};
-        leaf_bounds(s, n.left, l0, h0);
-        if (n.right != MRT_REF_NONE) leaf_bounds(s, n.right, l1, h1);
-        DNode& o = nodes[i];
-        o.xy0 = make_float4(l0[0], h0[0], l0[1], h0[1]);
-        o.xy1 = make_float4(l1[0], h1[0], l1[1], h1[1]);
-        o.z01 = make_float4(l0[2], h0[2], l1[2], h1[2]);
-        o.child0 = n.left;
-        o.child1 = n.right;
-        o.pad0 = o.pad1 = 0;
+    std::vector<DNode> nodes;
+    std::vector<uint32_t> tri_map(s->n_tris);      // device triangle index -> caller's triangle index
+    std::vector<uint32_t> blas_root(s->n_blas);
+    std::vector<uint32_t> roots(s->roots, s->roots + s->n_roots);
+    auto set_child = [&](DNode& o, int which, uint32_t ref, const float lo[3], const float hi[3]) {
+        if (which == 0) {
+            o.xy0 = make_float4(lo[0], hi[0], lo[1], hi[1]);
+            o.z01.x = lo[2]; o.z01.y = hi[2];
+            o.child0 = ref;
+        } else {
+            o.xy1 = make_float4(lo[0], hi[0], lo[1], hi[1]);
+            o.z01.z = lo[2]; o.z01.w = hi[2];
+            o.child1 = ref;
+        }
+    };
+    const float empty_lo[3] = {inf, inf, inf}, empty_hi[3] = {-inf, -inf, -inf};
+    int max_tlas_depth = tlas_depth, max_blas_depth = blas_depth;
+    if (keep) {
+        nodes.resize(s->n_nodes);
+        for (uint64_t i = 0; i < s->n_nodes; ++i) {
+            const mrt_node& n = s->nodes[i];
+            float l0[3], h0[3], l1[3] = {inf, inf, inf}, h1[3] = {-inf, -inf, -inf};
+            leaf_bounds(s, n.left, l0, h0);
+            if (n.right != MRT_REF_NONE) leaf_bounds(s, n.right, l1, h1);
+            DNode& o = nodes[i];
+            o.pad0 = o.pad1 = 0;
+            set_child(o, 0, n.left, l0, h0);   // a TRIANGLE ref here is a one-triangle leaf (count bits 0, index < 2^27)
+            set_child(o, 1, n.right, l1, h1);
+        }
+        for (uint64_t i = 0; i < s->n_tris; ++i) tri_map[i] = (uint32_t)i;
+        for (uint64_t i = 0; i < s->n_blas; ++i) blas_root[i] = s->blas[i].root;
+    } else {
+        // emit a built subtree as DNodes; returns the reference its parent stores. leaf_ref(first, count) names a leaf.
+        struct Emit {
+            std::vector<DNode>& out;
+            const mrt_build::Builder& b;
+            std::function<uint32_t(uint32_t, uint32_t)> leaf_ref;
+            decltype(set_child)& set;
+            uint32_t run(int32_t i) {
+                const mrt_build::Node& n = b.nodes[(size_t)i];
+                if (n.left < 0) return leaf_ref(n.first, n.count);
+                const uint32_t me = (uint32_t)out.size();
+                out.push_back(DNode{});
+                uint32_t l = run(n.left), r = run(n.right);
+                DNode o{};
+                set(o, 0, l, b.nodes[(size_t)n.left].lo, b.nodes[(size_t)n.left].hi);
+                set(o, 1, r, b.nodes[(size_t)n.right].lo, b.nodes[(size_t)n.right].hi);
+                out[me] = o;
+                return MRT_REF(MRT_PRIM_NODE, me);
+            }
+        };
+        auto emit_tree = [&](mrt_build::Builder& b, int32_t root, std::function<uint32_t(uint32_t, uint32_t)> leaf_ref) -> uint32_t {
+            Emit e{nodes, b, leaf_ref, set_child};
+            if (b.nodes[(size_t)root].left < 0) {  // the whole set is one leaf: still needs a node to hold its box
+                const uint32_t me = (uint32_t)nodes.size();
+                DNode o{};
+                set_child(o, 0, leaf_ref(b.nodes[(size_t)root].first, b.nodes[(size_t)root].count), b.nodes[(size_t)root].lo, b.nodes[(size_t)root].hi);
+                set_child(o, 1, kNone, empty_lo, empty_hi);
+                nodes.push_back(o);
+                return MRT_REF(MRT_PRIM_NODE, me);
+            }
+            return e.run(root);
+        };
+        max_blas_depth = 0;
+        for (uint64_t bi = 0; bi < s->n_blas; ++bi) {  // BLAS: SAH, leaves of up to 4 triangles
+            const mrt_blas& bl = s->blas[bi];
+            std::vector<mrt_build::Prim> prims(bl.n_tris);
+            for (uint32_t i = 0; i < bl.n_tris; ++i) {
+                prims[i].ref = bl.first_tri + i;
+                leaf_bounds(s, MRT_REF(MRT_PRIM_TRIANGLE, bl.first_tri + i), prims[i].lo, prims[i].hi);
+            }
+            mrt_build::Builder b(prims, 4, 40, 1.0f);
+            int32_t root = b.build(0, prims.size(), 0);
+            max_blas_depth = std::max(max_blas_depth, std::max(b.depth_of(root), 1));
+            for (uint32_t i = 0; i < bl.n_tris; ++i) tri_map[bl.first_tri + i] = prims[i].ref;  // device order = leaf order, inside the BLAS's own range
+            const uint32_t base = bl.first_tri;
+            blas_root[bi] = emit_tree(b, root, [base](uint32_t first, uint32_t count) { return MRT_REF(MRT_PRIM_TRIANGLE, base + first) | ((count - 1u) << 27); });
+        }
+        max_tlas_depth = 0;
+        for (uint32_t ri = 0; ri < s->n_roots; ++ri) {  // TLAS: every root that is a BVH is rebuilt over its own leaves, one object per leaf
+            if (MRT_REF_KIND(roots[ri]) != MRT_PRIM_NODE) continue;
+            std::vector<mrt_build::Prim> prims;
+            std::vector<uint32_t> st{roots[ri]};
+            while (!st.empty()) {
+                uint32_t ref = st.back();
+                st.pop_back();
+                if (MRT_REF_KIND(ref) == MRT_PRIM_NODE) {
+                    const mrt_node& n = s->nodes[MRT_REF_INDEX(ref)];
+                    if (n.right != MRT_REF_NONE) st.push_back(n.right);
+                    st.push_back(n.left);
+                } else {
+                    mrt_build::Prim p;
+                    p.ref = ref;
+                    leaf_bounds(s, ref, p.lo, p.hi);
+                    prims.push_back(p);
+                }
+            }
+            mrt_build::Builder b(prims, 1, 28, 4.0f);
+            int32_t root = b.build(0, prims.size(), 0);
+            max_tlas_depth = std::max(max_tlas_depth, std::max(b.depth_of(root), 1));
+            const std::vector<mrt_build::Prim>* pp = &prims;
+            roots[ri] = emit_tree(b, root, [pp](uint32_t first, uint32_t) { return (*pp)[first].ref; });
+        }
+        if (max_tlas_depth + max_blas_depth + 2 + (int)std::min<uint32_t>(s->n_roots, 8) > kStackSize)
+            return fail(ctx, MRT_E_UNSUPPORTED, "rebuilt BVH too deep for the traversal stack");
     }
+    // which triangles can fail Material::alpha_test (geom.rs:567-571): UV'd, and their own material's surface can return alpha 0
+    std::vector<int8_t> surf_alpha(s->n_surfaces, -1), mat_alpha(s->n_materials, -1);
+    std::function<bool(int32_t)> surface_can_be_transparent = [&](int32_t si) -> bool {
+        if (surf_alpha[(size_t)si] >= 0) return surf_alpha[(size_t)si] != 0;
+        const mrt_surface& u = s->surfaces[si];
+        bool r = true;
+        if (u.kind == MRT_SURF_SOLID) r = u.color[3] == 0.0f;
+        else if (u.kind == MRT_SURF_YCBCR) r = false;  // alpha is always 1 (texture.rs:246)
+        else if (u.kind == MRT_SURF_TEXTURE) {
+            const mrt_texture& t = s->textures[u.a];
+            r = false;
+            for (uint64_t k = 0; k < (uint64_t)t.width * t.height && !r; ++k) r = s->texels[4 * (t.texel_offset + k) + 3] == 0.0f;
+        }
+        surf_alpha[(size_t)si] = r ? 1 : 0;
+        return r;
+    };
+    std::function<bool(int32_t)> material_can_fail_alpha = [&](int32_t mi) -> bool {
+        if (mat_alpha[(size_t)mi] >= 0) return mat_alpha[(size_t)mi] != 0;
+        const mrt_material& m = s->materials[mi];
+        bool r = false;
+        if (m.kind == MRT_MAT_LAMBERTIAN || m.kind == MRT_MAT_METAL || m.kind == MRT_MAT_SPECULAR) r = surface_can_be_transparent(m.surface);
+        else if (m.kind == MRT_MAT_MIX) r = material_can_fail_alpha(m.left) || material_can_fail_alpha(m.right);
+        mat_alpha[(size_t)mi] = r ? 1 : 0;
+        return r;
+    };
     std::vector<float4> spheres(s->n_spheres);
     std::vector<DSphereAux> saux(s->n_spheres);
     for (uint64_t i = 0; i < s->n_spheres; ++i) {
@@ -758,9 +882,16 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         saux[i] = DSphereAux{s->spheres[i].material, s->spheres[i].object_id};
     }
     std::vector<DTriVerts> tv(s->n_tris);
+    uint32_t any_alpha = 0;
     for (uint64_t i = 0; i < s->n_tris; ++i) {
-        const float* v = s->tri_verts + 9 * i;
-        tv[i].a = make_float4(v[0], v[1], v[2], 0.0f);
+        const uint32_t orig = tri_map[i];
+        const float* v = s->tri_verts + 9 * (size_t)orig;
+        const mrt_tri_shading& sh = s->tri_shading[orig];
+        uint32_t flags = ((sh.flags & MRT_TRI_HAS_UV) && material_can_fail_alpha(sh.material)) ? kTriAlphaFlag : 0u;
+        any_alpha |= flags;
+        float fw;
+        std::memcpy(&fw, &flags, 4);
+        tv[i].a = make_float4(v[0], v[1], v[2], fw);
         tv[i].b = make_float4(v[3], v[4], v[5], 0.0f);
         tv[i].c = make_float4(v[6], v[7], v[8], 0.0f);
     }
@@ -776,7 +907,7 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         std::memset(&o, 0, sizeof o);
         pack(in.inv_transform, o.inv0, o.inv1, o.inv2);
         pack(in.transform, o.fwd0, o.fwd1, o.fwd2);
-        o.root = s->blas[in.blas].root;
+        o.root = blas_root[in.blas];
         o.material = in.material;
         o.flags = in.flags;
         o.object_id = in.object_id;
@@ -787,6 +918,7 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if ((rc = upload(ctx, spheres.data(), spheres.size(), &d.spheres))) return rc;
     if ((rc = upload(ctx, saux.data(), saux.size(), &d.sphere_aux))) return rc;
     if ((rc = upload(ctx, tv.data(), tv.size(), &d.tri_verts))) return rc;
+    if ((rc = upload(ctx, tri_map.data(), tri_map.size(), &d.tri_map))) return rc;
     if ((rc = upload(ctx, s->tri_shading, (size_t)s->n_tris, &d.tri_shading))) return rc;
     if ((rc = upload(ctx, inst.data(), inst.size(), &d.instances))) return rc;
     if ((rc = upload(ctx, s->blas, (size_t)s->n_blas, &d.blas))) return rc;
@@ -797,10 +929,11 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if ((rc = upload(ctx, reinterpret_cast<const float4*>(s->texels), (size_t)s->n_texels, &d.texels))) return rc;
     d.n_roots = s->n_roots;
     d.n_volumes = (uint32_t)s->n_volumes;
+    d.has_alpha = any_alpha;
     d.roots_ext = nullptr;
     if (s->n_roots <= 8) {
-        for (uint32_t i = 0; i < s->n_roots; ++i) d.roots[i] = s->roots[i];
-    } else if ((rc = upload(ctx, s->roots, (size_t)s->n_roots, &d.roots_ext))) {
+        for (uint32_t i = 0; i < s->n_roots; ++i) d.roots[i] = roots[i];
+    } else if ((rc = upload(ctx, roots.data(), roots.size(), &d.roots_ext))) {
         return rc;
     }
     d.bg = s->background;
@@ -849,7 +982,8 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
     RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst};
-    k_aov<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    if (ctx->scene.has_alpha) k_aov<true><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    else k_aov<false><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     AOV_TRY(cudaGetLastError());
     if (albedo) AOV_TRY(cudaMemcpyAsync(albedo, d_alb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
     if (normal) AOV_TRY(cudaMemcpyAsync(normal, d_nrm, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
@@ -939,8 +1073,11 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[0], ctx->stream));
             k_generate<<<ctx->grid_generate, 256, 0, ctx->stream>>>(ctx->cam, rp, pool, ctx->d_q, cur);
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[1], ctx->stream)); MRT_CUDA(cudaEventRecord(e[2], ctx->stream)); }
-            if (ctx->opt_count) k_extend<true><<<ctx->grid_extend_count, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
-            else k_extend<false><<<ctx->grid_extend, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            const bool alpha = ctx->scene.has_alpha != 0;
+            if (ctx->opt_count && alpha) k_extend<true, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            else if (ctx->opt_count) k_extend<true, false><<<ctx->grid_extend_count, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            else if (alpha) k_extend<false, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            else k_extend<false, false><<<ctx->grid_extend, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
             k_shade<<<ctx->grid_shade, 256, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));

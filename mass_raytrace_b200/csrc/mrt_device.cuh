@@ -15,7 +15,10 @@
 namespace mrt {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kStackSize = 64;
+constexpr int kStackSize = 96;
+// device-side triangle leaf reference: kind TRIANGLE | (count-1) << 27 | first triangle (device order, 27 bits)
+constexpr uint32_t kTriIndexMask = 0x07FFFFFFu;
+constexpr uint32_t kTriAlphaFlag = 1u;  // DTriVerts.a.w (as bits): the triangle's own material can fail alpha_test (geom.rs:568)
 
 // ---- device scene (HBM layout; all arrays 16-byte aligned, fetched with 128-bit loads) -----------------------
 // Inner node, 64 B = one half cache line: both children's AABBs + both child refs, so one fetch decides both
@@ -46,8 +49,9 @@ struct DScene {
     const DNode* nodes;
     const float4* spheres;  // center.xyz, radius
     const DSphereAux* sphere_aux;
-    const DTriVerts* tri_verts;
-    const mrt_tri_shading* tri_shading;
+    const DTriVerts* tri_verts;          // device (BVH leaf) order
+    const uint32_t* tri_map;             // device triangle index -> caller's triangle index
+    const mrt_tri_shading* tri_shading;  // caller's order
     const DInstance* instances;
     const mrt_blas* blas;
     const mrt_volume* volumes;
@@ -58,6 +62,7 @@ struct DScene {
     uint32_t roots[8];
     uint32_t n_roots;
     uint32_t n_volumes;
+    uint32_t has_alpha;                  // some triangle carries kTriAlphaFlag: the ALPHA kernel variants are used
     const uint32_t* roots_ext;  // when n_roots > 8
     mrt_background bg;
 };
@@ -338,21 +343,30 @@ __device__ __forceinline__ void trav_node(const DScene& sc, Traversal& T, uint32
     }
 }
 
-template <bool COUNT>
+// Material::alpha_test of the triangle's OWN material at the candidate hit (geom.rs:567-571); defined after the surfaces below
+__device__ bool triangle_alpha_test(const DScene& sc, const DTriVerts& tv, uint32_t tri_dev, const Ray& r, float t, const RngKey& key);
+
+template <bool COUNT, bool ALPHA>
 __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32_t* stack, float t_min, const RngKey& key, VisitCounters* cnt) {
     const uint32_t ref = T.ref;
     const uint32_t idx = MRT_REF_INDEX(ref);
     T.ref = kNone;
     switch (MRT_REF_KIND(ref)) {
         case MRT_PRIM_TRIANGLE: {
-            if (COUNT) cnt->tri_tests++;
-            const DTriVerts* tp = &sc.tri_verts[idx];
-            DTriVerts tv;
-            tv.a = __ldg(&tp->a);
-            tv.b = __ldg(&tp->b);
-            tv.c = __ldg(&tp->c);
-            float t;
-            if (triangle_test(tv, T.r, t_min, T.best.t, t)) T.best = HitRec{t, ref, T.cur_inst};
+            const uint32_t first = ref & kTriIndexMask, count = ((ref >> 27) & 3u) + 1u;
+            for (uint32_t k = 0; k < count; ++k) {
+                if (COUNT) cnt->tri_tests++;
+                const DTriVerts* tp = &sc.tri_verts[first + k];
+                DTriVerts tv;
+                tv.a = __ldg(&tp->a);
+                tv.b = __ldg(&tp->b);
+                tv.c = __ldg(&tp->c);
+                float t;
+                if (triangle_test(tv, T.r, t_min, T.best.t, t)) {
+                    if (ALPHA && (__float_as_uint(tv.a.w) & kTriAlphaFlag) && !triangle_alpha_test(sc, tv, first + k, T.r, t, key)) continue;  // geom.rs:567-571
+                    T.best = HitRec{t, MRT_REF(MRT_PRIM_TRIANGLE, first + k), T.cur_inst};
+                }
+            }
             break;
         }
         case MRT_PRIM_SPHERE: {
@@ -390,7 +404,7 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
 }
 
 // run a traversal to completion (AOV pass)
-template <bool COUNT>
+template <bool COUNT, bool ALPHA>
 __device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, float t_min, float t_max, const RngKey& key, VisitCounters* cnt) {
     uint32_t stack[kStackSize];
     Traversal T;
@@ -398,7 +412,7 @@ __device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, f
     while (trav_pop(sc, T, stack)) {
         while (T.ref != kNone) {
             if (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, t_min, cnt);
-            else trav_leaf<COUNT>(sc, T, stack, t_min, key, cnt);
+            else trav_leaf<COUNT, ALPHA>(sc, T, stack, t_min, key, cnt);
         }
     }
     if (T.best.prim == kNone) T.best.t = t_max;
@@ -481,6 +495,31 @@ __device__ __noinline__ V4 surface_get_slow(const DScene& sc, int surface, float
     }
 }
 
+// Triangle::intersect's alpha test (geom.rs:535-571): area barycentrics -> uv -> alpha_test of the triangle's own material
+// (Lambertian / Metal / Specular: surface alpha != 0, material.rs:222-224, 281-283, 380-382; Mix: a coin flip then the child,
+// :419-425; every other material: the default `true`, :24-26).
+__device__ __noinline__ bool triangle_alpha_test(const DScene& sc, const DTriVerts& tv, uint32_t tri_dev, const Ray& r, float t, const RngKey& key) {
+    const mrt_tri_shading& sh = sc.tri_shading[sc.tri_map[tri_dev]];
+    V3 va = v3(tv.a), vb = v3(tv.b), vc = v3(tv.c);
+    V3 point = ray_at(r, t);
+    V3 d0 = va - point, d1 = vb - point, d2 = vc - point;
+    float area = length(cross(va - vb, va - vc));
+    float a0 = length(cross(d1, d2)) / area;
+    float a1 = length(cross(d2, d0)) / area;
+    float a2 = length(cross(d0, d1)) / area;
+    float u = (sh.uv[0] * a0 + sh.uv[2] * a1) + sh.uv[4] * a2;
+    float v = (sh.uv[1] * a0 + sh.uv[3] * a1) + sh.uv[5] * a2;
+    mrt_material mat = sc.materials[sh.material];
+    uint32_t level = 0;
+    while (mat.kind == MRT_MAT_MIX && level < 16) {
+        Rand4 c = draw4(key, kStreamAlpha + ((tri_dev & 0xFFFFu) << 4) + level);
+        mat = sc.materials[(c.x < mat.p[0]) ? mat.left : mat.right];
+        ++level;
+    }
+    if (mat.kind == MRT_MAT_LAMBERTIAN || mat.kind == MRT_MAT_METAL || mat.kind == MRT_MAT_SPECULAR) return surface_get(sc, mat.surface, u, v).w != 0.0f;
+    return true;
+}
+
 // ---- closest-hit attributes (the part of Hit the reference fills for every candidate; here once) -----------------
 struct Surfel {
     V3 point, normal;
@@ -501,7 +540,7 @@ __device__ __forceinline__ int32_t hit_material(const DScene& sc, const HitRec& 
         case MRT_PRIM_VOLUME: return sc.volumes[idx].material;
         case MRT_PRIM_TRIANGLE: {
             int32_t m = (h.inst != kNone) ? sc.instances[h.inst].material : -1;
-            return m >= 0 ? m : sc.tri_shading[idx].material;
+            return m >= 0 ? m : sc.tri_shading[sc.tri_map[h.prim & kTriIndexMask]].material;
         }
         default: return -1;
     }
@@ -537,9 +576,10 @@ __device__ __forceinline__ Surfel resolve_hit(const DScene& sc, const Ray& world
             uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
             in.flags = meta.z;
             Ray r = to_instance_space(in, world);
-            const DTriVerts* tp = &sc.tri_verts[idx];
+            const uint32_t tri_dev = h.prim & kTriIndexMask, tri = sc.tri_map[tri_dev];
+            const DTriVerts* tp = &sc.tri_verts[tri_dev];
             V3 va = v3(__ldg(&tp->a)), vb = v3(__ldg(&tp->b)), vc = v3(__ldg(&tp->c));
-            const mrt_tri_shading& sh = sc.tri_shading[idx];
+            const mrt_tri_shading& sh = sc.tri_shading[tri];
             V3 point = ray_at(r, h.t);
             V3 d0 = va - point, d1 = vb - point, d2 = vc - point;
             float area = length(cross(va - vb, va - vc));
@@ -562,7 +602,7 @@ __device__ __forceinline__ Surfel resolve_hit(const DScene& sc, const Ray& world
                 s.normal = unit(xform(in.fwd0, in.fwd1, in.fwd2, s.normal, 0.0f));
             }
             s.object_id = meta.w;
-            s.tri_id = idx - sc.blas[ip->pad[0]].first_tri;
+            s.tri_id = tri - sc.blas[ip->pad[0]].first_tri;
             break;
         }
     }

@@ -21,8 +21,13 @@ Y = np.array([0.2126, 0.7152, 0.0722], np.float32)
 NONE = 0xFFFFFFFF
 
 
-def check_aov(g, o, exclude=None, albedo_exact=True, max_ties=16):
-    """ids exact except exact-t ties; t, normal within 1e-5 relative (and almost everywhere bit-identical)."""
+def check_aov(g, o, exclude=None, albedo_exact=True, max_ties=None):
+    """ids exact except exact-t ties; t, normal within 1e-5 relative (and almost everywhere bit-identical).
+    An exact tie = a pixel centre exactly on an edge shared by two primitives (e.g. the diagonal of a cube face): both candidates
+    have the same t and the winner depends on the order the tree is walked in, which the north star excludes from the comparison.
+    max_ties=None allows up to 0.5 % of the pixels to be such ties (the SAH rebuild walks a different tree than the oracle)."""
+    if max_ties is None:
+        max_ties = int(0.005 * g["object"].size)
     keep = np.ones(g["object"].shape, bool) if exclude is None else ~exclude
     ids_differ = ((g["object"] != o["object"]) | (g["tri"] != o["tri"])) & keep
     both_hit = np.isfinite(g["t"]) & np.isfinite(o["t"])
@@ -33,6 +38,7 @@ def check_aov(g, o, exclude=None, albedo_exact=True, max_ties=16):
     # a primitive-id mismatch is allowed only on an exact tie: same t (<= 1e-6 relative), two candidate primitives
     assert ids_differ.sum() <= max_ties, f"{ids_differ.sum()} id mismatches"
     assert (rel[ids_differ] <= 1e-6).all(), "id mismatch that is not a tie"
+    assert (g["t"][ids_differ] == o["t"][ids_differ]).mean() >= 0.99 if ids_differ.any() else True
     same = keep & ~ids_differ
     nerr = np.abs(g["normal"].astype(np.float64) - o["normal"]).max(-1)
     assert nerr[same].max() <= 1e-5, f"normal differs by {nerr[same].max():.3g}"
@@ -63,12 +69,13 @@ def mesh_ply(tmp_mesh_dir):
 # ------------------------------------------------------------------------------------------------------------------
 # test 1: primary rays
 # ------------------------------------------------------------------------------------------------------------------
-def test_aov_cornell(renderer):
+@pytest.mark.parametrize("keep_topology", [False, True])
+def test_aov_cornell(renderer, keep_topology):
     world, camera = scenes.cornell_box(1.0)
-    renderer.set_scene(NativeScene(world, camera))
+    renderer.set_scene(NativeScene(world, camera), keep_topology=keep_topology)
     g = renderer.render_aov(512, 512)
     o = OracleScene(world, camera).render_aov(512, 512)
-    ties, frac = check_aov(g, o)
+    ties, frac = check_aov(g, o, max_ties=16 if keep_topology else None)
     assert frac == 1.0
 
 
@@ -79,12 +86,13 @@ def test_aov_cornell_golden(renderer):
     h, w = gold["aov_object"].shape
     g = renderer.render_aov(w, h)
     o = dict(object=gold["aov_object"], tri=gold["aov_tri"], t=gold["aov_t"], normal=gold["aov_normal"], albedo=gold["aov_albedo"])
-    check_aov(g, o)
+    check_aov(g, o, max_ties=int(0.02 * w * h))  # a 64x64 symmetric view puts many pixel centres exactly on cube-face diagonals
 
 
-def test_aov_book1(renderer):
+@pytest.mark.parametrize("keep_topology", [False, True])
+def test_aov_book1(renderer, keep_topology):
     world, camera = scenes.book1_spheres(1.5, aperture=0.0)
-    renderer.set_scene(NativeScene(world, camera))
+    renderer.set_scene(NativeScene(world, camera), keep_topology=keep_topology)
     g = renderer.render_aov(600, 400)
     o = OracleScene(world, camera).render_aov(600, 400)
     ties, frac = check_aov(g, o, albedo_exact=False)
@@ -105,19 +113,21 @@ def test_aov_sphere_grid(renderer):
     check_aov(g, o)
 
 
-def test_aov_instanced_mesh_field(renderer, mesh_ply):
+@pytest.mark.parametrize("keep_topology", [False, True])
+def test_aov_instanced_mesh_field(renderer, mesh_ply, keep_topology):
     path, md, n = mesh_ply
     world, camera = scenes.lucy_layout(path, md, grid=2)  # 25 rotated, scaled instances of one 65k-triangle BLAS
-    renderer.set_scene(NativeScene(world, camera))
+    renderer.set_scene(NativeScene(world, camera), keep_topology=keep_topology)
     g = renderer.render_aov(640, 360)
     o = OracleScene(world, camera).render_aov(640, 360)
     check_aov(g, o)
     assert (g["tri"] != NONE).mean() > 0.3
 
 
-def test_aov_book2_with_uv_mesh_texture_and_volumes(renderer):
+@pytest.mark.parametrize("keep_topology", [False, True])
+def test_aov_book2_with_uv_mesh_texture_and_volumes(renderer, keep_topology):
     world, camera = scenes.book2_final(boxes_per_side=12, n_cluster=200)
-    renderer.set_scene(NativeScene(world, camera))
+    renderer.set_scene(NativeScene(world, camera), keep_topology=keep_topology)
     g = renderer.render_aov(480, 270)
     o = OracleScene(world, camera).render_aov(480, 270)
     # Volume hits depend on the free-flight random (geom.rs:638): excluded wherever either side reports a Volume
@@ -161,7 +171,7 @@ def test_aov_full_size_million_triangle_mesh(renderer, tmp_mesh_dir):
     renderer.set_scene(host)
     g = renderer.render_aov(1920, 1080)
     o = OracleScene(world, camera).render_aov(1920, 1080)
-    ties, frac = check_aov(g, o, max_ties=64)
+    ties, frac = check_aov(g, o)
     assert (g["tri"] != NONE).mean() > 0.2
 
 
@@ -458,6 +468,70 @@ def test_closed_form_samplers_match_rejection_sampler_distributions(renderer, or
     assert ks(np.linalg.norm(gb, axis=1), np.linalg.norm(ob, axis=1)) < crit
     assert ks(np.linalg.norm(gd, axis=1), np.linalg.norm(od, axis=1)) < crit
     assert ks(np.arctan2(gs[:, 1], gs[:, 0]), np.arctan2(os_[:, 1], os_[:, 0])) < crit
+
+
+def test_alpha_tested_triangles(renderer):
+    """Triangle::intersect rejects a candidate whose own material fails alpha_test (geom.rs:567-571; Lambertian: texel alpha != 0,
+    material.rs:222-224) and traversal continues behind it: holes in a textured mesh must match the oracle exactly."""
+    rs = np.random.RandomState(11)
+    px = rs.randint(0, 256, (16, 16, 4)).astype(np.uint8)
+    px[..., 3] = 255
+    px[:, (np.arange(16) // 4) % 2 == 0, 3] = 0  # transparent stripes 4 texels wide: bilinear alpha is exactly 0 inside them
+    cam = Camera(35.0, V3(0, 1.5, 5), V3(0, 1, 0), V3(0, 1, 0), 1.5, 0.0, 5.0)
+
+    def build(tex):
+        holes = Lambertian(Texture(tex, WRAP_CLAMP))
+        w = World(SkyBackground())
+        w.add(Model(scenes.uv_sphere_triangles((0.0, 1.0, 0.0), 1.0, 32, 16, material=holes)))
+        w.add(Model(scenes.uv_sphere_triangles((0.3, 1.0, -2.5), 1.0, 24, 12, material=Mix(0.5, holes, Metal(0.0, SolidColor((1, 1, 1, 1)))))))
+        w.add(Sphere(Lambertian(SolidColor((0.8, 0.2, 0.2, 1))), V3(0, -1000, 0), 1000.0))
+        w.build_bvh()
+        return w
+
+    opaque = px.copy()
+    opaque[..., 3] = 255
+    renderer.set_scene(NativeScene(build(opaque), cam))
+    solid = renderer.render_aov(360, 240)
+    w = build(px)
+    for keep in (False, True):
+        renderer.set_scene(NativeScene(w, cam), keep_topology=keep)
+        g = renderer.render_aov(360, 240)
+        o = OracleScene(w, cam).render_aov(360, 240)
+        # the second mesh's Mix material flips a coin per candidate (material.rs:419-425): compare only pixels where neither side's
+        # nearest surface is that mesh
+        clean = (g["object"] != 1) & (o["object"] != 1)
+        check_aov(g, o, exclude=~clean, albedo_exact=False)
+        # covered by mesh 0 when opaque; now the ray passes a hole and ends on the far inside wall, the ground, mesh 1 or the sky
+        def through(a):
+            return (solid["object"] == 0) & ((a["object"] != 0) | (a["t"] > solid["t"] * 1.05))
+
+        assert through(g).sum() > 1500 and ((solid["object"] == 0) & ~through(g)).sum() > 1500
+        assert np.array_equal(through(g) & clean, through(o) & clean)
+    stat_compare(renderer, w, cam, 72, 48, 96)
+
+
+def test_sah_rebuild_visits_fewer_nodes(renderer, mesh_ply):
+    """The library's SAH rebuild and the caller's median-split topology give the same image bit for bit (no ties in this scene's
+    sample set would be luck -- compare statistically identical AOVs instead) and the rebuild must not visit more nodes."""
+    path, md, n = mesh_ply
+    world, camera = scenes.lucy_layout(path, md, grid=1)
+    host = NativeScene(world, camera)
+    visits = {}
+    images = {}
+    for keep in (True, False):
+        renderer.set_scene(host, keep_topology=keep)
+        renderer.set_option(renderer.OPT_COUNT_VISITS, 1)
+        try:
+            images[keep] = renderer.render(160, 90, 8, 50, seed=5)
+            st = renderer.stats()
+        finally:
+            renderer.set_option(renderer.OPT_COUNT_VISITS, 0)
+        visits[keep] = (st["node_visits"] / st["rays"], st["tri_tests"] / st["rays"])
+        assert st["node_visits"] > 0 and st["tri_tests"] > 0
+    # same samples, same primitives: identical sums unless an exact tie was resolved differently (rare) -> allow a handful of pixels
+    assert (images[True][0] != images[False][0]).any(-1).mean() < 1e-3
+    assert np.array_equal(images[True][1].sum(), images[False][1].sum()) or abs(int(images[True][1].sum()) - int(images[False][1].sum())) < 50
+    assert visits[False][0] < visits[True][0], visits
 
 
 # ------------------------------------------------------------------------------------------------------------------
