@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(_HERE, "libmrt_cuda.so")
+CUDA_LIB_PATH = os.environ.get("MRT_CUDA_LIB", os.path.join(_HERE, "libmrt_cuda.so"))  # override only for kernel-variant experiments
 HOST_LIB_PATH = os.path.join(_HERE, "libmrt_host.so")
 
 u8p = C.POINTER(C.c_uint8)

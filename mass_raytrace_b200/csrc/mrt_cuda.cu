@@ -304,7 +304,13 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
         atomicAdd(reinterpret_cast<unsigned long long*>(&accum[(size_t)pixel * 4 + 3]), (unsigned long long)bounce);
 }
 
-__global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
+#ifndef MRT_SHADE_THREADS
+#define MRT_SHADE_THREADS 256
+#endif
+#ifndef MRT_SHADE_MINB
+#define MRT_SHADE_MINB 3
+#endif
+__global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
                                                QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
     uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
     for (uint32_t kind = 0; kind < Q_COUNT; ++kind) {
@@ -324,6 +330,35 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ DScene
             at = warp_append(&q->n_free, valid && !cont);
             if (valid && !cont) pool.free_list[at] = slot;
         }
+    }
+}
+
+// MRT_OPT_SHADE_INORDER (measurement aid, off by default): shade in slot order -- coalesced 64-byte records but mixed material
+// kinds per warp -- instead of through the material-sorted index queues. Bit-identical images; 2x SLOWER on B200 (Cornell 21.9 vs
+// 11.1 ms, book-1 7.6 vs 3.1 ms per render), which is the measured case for material-sorted shading (profiles/README.md).
+constexpr uint32_t kProcessed = 0xFFFFFFFDu;
+__global__ void k_mark_processed(Pool pool) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pool.slots; i += gridDim.x * blockDim.x) pool.slot[i].hit.y = kProcessed;
+}
+__global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade_inorder(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp,
+                                                                                     Pool pool, QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
+    uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
+    const uint32_t n_round = (pool.slots + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool valid = i < pool.slots, cont = false;
+        if (valid) {
+            uint4 hr = pool.slot[i].hit;
+            valid = hr.y != kProcessed;
+            if (valid) {
+                uint32_t kind = (hr.y == kNone) ? (uint32_t)Q_MISS : Q_FIRST_MAT + (uint32_t)sc.materials[(int32_t)hr.w].kind;
+                shade_entry(sc, rp, pool, accum, nonfinite, kind, i, cont);
+                pool.slot[i].hit.y = kProcessed;
+            }
+        }
+        uint32_t at = warp_append(&q->n_next, valid && cont);
+        if (valid && cont) q_next[at] = i;
+        at = warp_append(&q->n_free, valid && !cont);
+        if (valid && !cont) pool.free_list[at] = i;
     }
 }
 
@@ -462,6 +497,7 @@ struct mrt_context {
     // options
     bool opt_count = false, opt_time = false;
     uint64_t opt_pool_slots = 0;
+    bool opt_shade_inorder = false;
     uint32_t opt_refill_lanes = kRefillLanes, opt_node_lanes = kNodeLanes, opt_node_burst = 1;
     mrt_stats stats{};
     int grid_extend = 0, grid_extend_count = 0, grid_extend_slow = 0, grid_shade = 0, grid_generate = 0;
@@ -569,7 +605,7 @@ int mrt_context_create(int device, void* stream, mrt_context** out) {
     ctx->grid_extend_count = ctx->n_sms * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, true>, 128, 0);
     ctx->grid_extend_slow = ctx->n_sms * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, MRT_SHADE_THREADS, 0);
     ctx->grid_shade = ctx->n_sms * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_generate, 256, 0);
     ctx->grid_generate = ctx->n_sms * std::max(occ, 1);
@@ -1059,6 +1095,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     MRT_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     MRT_CUDA(cudaMemcpyAsync(ctx->d_q, &ctx->h_q[2], sizeof(QueueState), cudaMemcpyHostToDevice, ctx->stream));
     k_iota<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(pool.free_list, pool.slots);
+    if (ctx->opt_shade_inorder) k_mark_processed<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(pool);
     st.kernel_launches++;
 
     std::vector<cudaEvent_t> tev;  // 6 events per iteration when kernel timing is on
@@ -1079,7 +1116,8 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
             else if (alpha) k_extend<false, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             else k_extend<false, false><<<ctx->grid_extend, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
-            k_shade<<<ctx->grid_shade, 256, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+            if (ctx->opt_shade_inorder) k_shade_inorder<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+            else k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));
             cur ^= 1;
             st.kernel_launches += 4;
@@ -1201,6 +1239,7 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             if (value < 1 || value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [1, 32]");
             ctx->opt_refill_lanes = (uint32_t)value;
             return MRT_OK;
+        case MRT_OPT_SHADE_INORDER: ctx->opt_shade_inorder = value != 0; return MRT_OK;
         case MRT_OPT_NODE_BURST:
             if (value < 1 || value > 64) return fail(ctx, MRT_E_INVALID, "burst out of range [1, 64]");
             ctx->opt_node_burst = (uint32_t)value;

@@ -1,0 +1,128 @@
+"""BASELINE.json configs at their full sizes (run with -m gpu). The oracle cannot finish these sizes in seconds, so each config
+is checked through size-independent properties -- exact split invariance of the sample range, the ray / bounce bookkeeping
+identity, finiteness -- plus agreement of the image means with an oracle render of the SAME scene at reduced resolution and spp
+(Mpaths/s and the expected pixel value do not depend on resolution)."""
+import os
+
+import numpy as np
+import pytest
+
+from mass_raytrace_b200 import NativeScene, scenes
+from oracle_backend import OracleScene
+
+pytestmark = pytest.mark.gpu
+Y = np.array([0.2126, 0.7152, 0.0722])
+
+
+def lum(rgb, spp):
+    return float((rgb.astype(np.float64) * Y).sum(-1).mean() / spp)
+
+
+def check_properties(renderer, w, h, spp, depth=50, seed=77, split=None):
+    rgb, b, count = renderer.render(w, h, spp, depth, seed=seed)
+    st = renderer.stats()
+    assert count == spp and rgb.shape == (h, w, 3) and b.shape == (h, w)
+    assert np.isfinite(rgb).all() and (rgb >= 0).all()
+    n = w * h * spp
+    total_b = int(b.astype(np.int64).sum())
+    assert st["paths"] == n
+    # rays = sum over samples of min(bounces + 1, depth): bounded by the bounce sums
+    assert total_b + n - total_b // depth <= st["rays"] <= total_b + n
+    assert int(b.max()) <= spp * depth
+    if split:
+        renderer.reset(w, h)
+        begin = 0
+        for part in split:
+            renderer.accumulate(begin, part, depth, seed=seed)
+            begin += part
+        assert begin == spp
+        rgb2, b2, count2 = renderer.download()
+        assert count2 == spp and np.array_equal(rgb2, rgb) and np.array_equal(b2, b)  # bit-identical for any split
+    return rgb, b, st
+
+
+def oracle_means(world, camera, w, h, spp, seed=5):
+    o = OracleScene(world, camera)
+    a = o.render(w, h, spp, 50, seed=seed)
+    c = o.render(w, h, spp, 50, seed=seed + 1)
+    la, lc = lum(a[0], spp), lum(c[0], spp)
+    ba, bc = a[1].mean() / spp, c[1].mean() / spp
+    return 0.5 * (la + lc), abs(la - lc), 0.5 * (ba + bc), abs(ba - bc)
+
+
+def assert_means(rgb, b, spp, om, rel=0.03):
+    lo, dl, bo, db = om
+    assert abs(lum(rgb, spp) - lo) <= max(rel * lo, 4 * dl), (lum(rgb, spp), lo, dl)
+    assert abs(b.mean() / spp - bo) <= max(rel * bo, 4 * db), (b.mean() / spp, bo, db)
+
+
+def test_cfg1_book1_1200x800_10spp(renderer):
+    world, camera = scenes.book1_spheres(1.5, aperture=0.1)
+    renderer.set_scene(NativeScene(world, camera))
+    rgb, b, st = check_properties(renderer, 1200, 800, 10, split=(4, 6))
+    assert_means(rgb, b, 10, oracle_means(world, camera, 300, 200, 40))
+    assert 2.5 < st["rays"] / st["paths"] < 3.6
+
+
+def test_cfg2_cornell_1024_1000spp(renderer):
+    world, camera = scenes.cornell_box(1.0)
+    renderer.set_scene(NativeScene(world, camera))
+    rgb, b, st = check_properties(renderer, 1024, 1024, 1000, split=(1, 499, 500))
+    # the oracle image must not be too small: u = (x + xi) / (W - 1) makes the field of view grow by 1/(W-1) (main.rs:258)
+    assert_means(rgb, b, 1000, oracle_means(world, camera, 256, 256, 32), rel=0.02)
+    assert 7.5 < st["rays"] / st["paths"] < 8.3
+    # converged enough to look at structure: the red wall is left, the green wall right (scenes/cornell.rs:46-53), light on top
+    mean = rgb / 1000
+    assert mean[512, 60, 0] > 5 * mean[512, 60, 1] and mean[512, 960, 1] > 5 * mean[512, 960, 0]
+    assert 7.5 < mean[880:910, 480:544].max() <= 8.0  # some pixels look straight at the emitter (8, 8, 8), seen edge-on below the ceiling
+
+
+@pytest.fixture(scope="module")
+def mesh1m(tmp_mesh_dir):
+    path = str(tmp_mesh_dir / "mesh_1m_full.ply")
+    n, md = scenes.write_synthetic_ply(path, 1024, 512, seed=1)
+    assert n == 1 << 20
+    world, camera = scenes.lucy_layout(path, md, grid=0)
+    return world, camera
+
+
+def test_cfg3_million_triangle_mesh_1920x1080_256spp(renderer, mesh1m):
+    world, camera = mesh1m
+    host = NativeScene(world, camera)
+    assert host.desc().contents.n_tris == (1 << 20) + 12
+    renderer.set_scene(host)
+    rgb, b, st = check_properties(renderer, 1920, 1080, 256, split=(100, 156))
+    assert st["scene_bytes"] > 150e6
+    assert_means(rgb, b, 256, oracle_means(world, camera, 240, 135, 32))
+
+
+def test_cfg4_book2_final_1920x1080_1000spp(renderer):
+    world, camera = scenes.book2_final()
+    assert len(world.objects) == 1024 + 1000 + 9  # boxes, cluster spheres, light + 5 spheres + 2 volumes + the textured mesh
+    renderer.set_scene(NativeScene(world, camera))
+    rgb, b, st = check_properties(renderer, 1920, 1080, 1000)
+    small = scenes.book2_final()
+    assert_means(rgb, b, 1000, oracle_means(*small, 320, 180, 16), rel=0.04)
+
+
+def test_cfg5_ten_meshes_4k_reduced_spp(renderer, tmp_mesh_dir):
+    """cfg 5's scene and resolution (10 x 1,048,576 triangles, 3840x2160); 32 of the 4096 spp so the test stays short -- the full
+    sample count only repeats the same kernels 128 times (bench.py --workload mesh10m runs it)."""
+    paths, mds = [], []
+    for i in range(10):
+        p = str(tmp_mesh_dir / f"mesh10m_{i}.ply")
+        n, md = scenes.write_synthetic_ply(p, 1024, 512, seed=100 + i)
+        paths.append(p)
+        mds.append(md)
+    world, camera = scenes.multi_mesh(paths, mds, 16.0 / 9.0)
+    host = NativeScene(world, camera)
+    assert host.desc().contents.n_tris == 10 * (1 << 20) + 12 and host.desc().contents.n_blas == 11
+    renderer.set_scene(host)
+    rgb, b, st = check_properties(renderer, 3840, 2160, 32, split=(16, 16))
+    assert st["scene_bytes"] > 1.5e9
+    aov = renderer.render_aov(3840, 2160)
+    hit_mesh = np.isin(aov["object"], np.arange(1, 11))
+    assert 0.05 < hit_mesh.mean() < 0.9 and len(np.unique(aov["object"][hit_mesh])) == 10
+    # every mesh hit carries a valid triangle index of its own 2^20-triangle mesh and a unit normal
+    assert aov["tri"][hit_mesh].max() < (1 << 20)
+    np.testing.assert_allclose(np.linalg.norm(aov["normal"][hit_mesh].astype(np.float64), axis=-1), 1.0, atol=1e-4)
