@@ -264,7 +264,8 @@ enum {
     MRT_OPT_REFILL_LANES = 4, /* k_extend: refill finished lanes when at least this many of a warp's 32 are idle */
     MRT_OPT_NODE_LANES = 5,   /* k_extend: run a node-visit phase when at least this many lanes are at an inner node; 0 = no voting (chain mode) */
     MRT_OPT_NODE_BURST = 6,   /* k_extend: node visits per lane per node phase */
-    MRT_OPT_SHADE_INORDER = 7 /* measurement aid: shade in slot order instead of through the material-sorted queues (slower) */
+    MRT_OPT_SHADE_INORDER = 7, /* measurement aid: shade in slot order instead of through the material-sorted queues (slower) */
+    MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 65536, 0 = off) */
 };
 int mrt_set_option(mrt_context* ctx, int option, uint64_t value);
 int mrt_get_stats(mrt_context* ctx, mrt_stats* out);

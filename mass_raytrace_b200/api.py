@@ -438,7 +438,7 @@ class MrtError(RuntimeError):
 class Renderer:
     """One GPU behind the C ABI of include/mrt.h. Replaces render() (main.rs:150-295); no CPU fallback."""
 
-    OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_POOL_SLOTS, OPT_REFILL_LANES, OPT_NODE_LANES, OPT_NODE_BURST, OPT_SHADE_INORDER = 1, 2, 3, 4, 5, 6, 7
+    OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_POOL_SLOTS, OPT_REFILL_LANES, OPT_NODE_LANES, OPT_NODE_BURST, OPT_SHADE_INORDER, OPT_FINISH_PATHS = 1, 2, 3, 4, 5, 6, 7, 8
 
     def __init__(self, device=0, stream=None):
         self.lib = _ffi.cuda_lib()

@@ -39,7 +39,7 @@ struct QueueState {
     uint32_t n_free;       // slots released by shade
     uint32_t ext_cursor;   // persistent-warp fetch cursor of extend
     uint32_t done;
-    uint32_t pad;
+    uint32_t finish_n;     // > 0: the drain has started; k_finish runs these last paths to completion in one launch
     uint32_t n_shade[Q_COUNT + 3];
     unsigned long long next_work, total_work, gen_base;
     unsigned long long rays, iterations;
@@ -50,6 +50,7 @@ struct RenderParams {
     uint32_t w, h, npix, spp_begin, max_depth;
     uint2 seed;
     uint32_t refill_lanes, node_lanes, node_burst;  // warp-vote thresholds of k_extend
+    uint32_t finish_paths;                          // drain threshold of k_finish (0 = never)
 };
 
 // One path = one 64-byte slot = two 32-byte sectors: extend reads sector 0 and writes `hit`; shade reads both and rewrites
@@ -99,7 +100,7 @@ __global__ void k_iota(uint32_t* p, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
 
-__global__ void k_advance(QueueState* q) {
+__global__ void k_advance(QueueState* q, uint32_t finish_paths) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     q->rays += q->n_ext;
     uint32_t n_cont = q->n_next;
@@ -110,12 +111,19 @@ __global__ void k_advance(QueueState* q) {
     q->gen_base = q->next_work;
     q->next_work += n_new;
     q->n_free = 0;
+    q->finish_n = 0;
+    if (remaining == 0 && n_cont > 0 && n_cont <= finish_paths) {
+        // the job is draining: no samples left to regenerate and only a few paths alive. Instead of up to max_depth more
+        // wavefront iterations over a nearly empty pool, k_finish runs each remaining path to its end in this iteration.
+        q->finish_n = n_cont;
+        n_cont = 0;
+    }
     q->n_cont = n_cont;
     q->n_new = n_new;
     q->n_ext = n_cont + n_new;
     q->ext_cursor = 0;
-    q->done = (n_cont + n_new == 0) ? 1u : 0u;
-    if (n_cont + n_new) q->iterations++;
+    q->done = (n_cont + n_new == 0 && q->finish_n == 0) ? 1u : 0u;
+    if (n_cont + n_new + q->finish_n) q->iterations++;
 }
 
 // Camera::ray world.rs:53-63 with the pixel jitter of main.rs:258-259 (jitter == false: pixel centres, main.rs:189-190)
@@ -310,25 +318,59 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
 #ifndef MRT_SHADE_MINB
 #define MRT_SHADE_MINB 3
 #endif
+#ifndef MRT_SHADE_UNROLL
+#define MRT_SHADE_UNROLL 2
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Each warp takes 32 x MRT_SHADE_UNROLL consecutive entries of one material queue: the slot indices are read first and the slot
+// records prefetched, so the gathers of the later entries overlap the shading of the earlier ones; the surviving / finished slots
+// of the whole chunk are appended to the next extend queue / the free list with ONE atomic each.
 __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
-                                               QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
+                                                                            QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
+    constexpr int U = MRT_SHADE_UNROLL;
     uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
+    const uint32_t lane = lane_id(), lt_mask = (1u << lane) - 1u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t kind = 0; kind < Q_COUNT; ++kind) {
         const uint32_t n = q->n_shade[kind];
         const uint32_t* __restrict__ queue = pool.q_shade + (size_t)kind * pool.slots;
-        const uint32_t n_round = (n + 31u) & ~31u;  // whole warps, so the ballots below see all 32 lanes
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-            const bool valid = i < n;
-            bool cont = false;
-            uint32_t slot = 0;
-            if (valid) {
-                slot = queue[i];
-                shade_entry(sc, rp, pool, accum, nonfinite, kind, slot, cont);
+        for (uint32_t base = warp * (32u * U); base < n; base += n_warps * (32u * U)) {
+            uint32_t slot[U];
+            bool valid[U], cont[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = base + (uint32_t)u * 32u + lane;
+                valid[u] = i < n;
+                slot[u] = valid[u] ? queue[i] : 0u;
+                if (valid[u]) prefetch_l2(&pool.slot[slot[u]]);
             }
-            uint32_t at = warp_append(&q->n_next, valid && cont);
-            if (valid && cont) q_next[at] = slot;
-            at = warp_append(&q->n_free, valid && !cont);
-            if (valid && !cont) pool.free_list[at] = slot;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cont[u] = false;
+                if (valid[u]) shade_entry(sc, rp, pool, accum, nonfinite, kind, slot[u], cont[u]);
+            }
+            uint32_t off_c[U], off_f[U], tot_c = 0, tot_f = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t mc = __ballot_sync(0xffffffffu, valid[u] && cont[u]), mf = __ballot_sync(0xffffffffu, valid[u] && !cont[u]);
+                off_c[u] = tot_c + __popc(mc & lt_mask);
+                off_f[u] = tot_f + __popc(mf & lt_mask);
+                tot_c += __popc(mc);
+                tot_f += __popc(mf);
+            }
+            uint32_t base_c = 0, base_f = 0;
+            if (lane == 0) {
+                if (tot_c) base_c = atomicAdd(&q->n_next, tot_c);
+                if (tot_f) base_f = atomicAdd(&q->n_free, tot_f);
+            }
+            base_c = __shfl_sync(0xffffffffu, base_c, 0);
+            base_f = __shfl_sync(0xffffffffu, base_f, 0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (valid[u] && cont[u]) q_next[base_c + off_c[u]] = slot[u];
+                if (valid[u] && !cont[u]) pool.free_list[base_f + off_f[u]] = slot[u];
+            }
         }
     }
 }
@@ -360,6 +402,39 @@ __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade_ino
         at = warp_append(&q->n_free, valid && !cont);
         if (valid && !cont) pool.free_list[at] = i;
     }
+}
+
+// Drain: one thread per remaining path, each looping extend + shade until its path ends (paths are independent, so no
+// grid-wide step is needed). Launched every iteration; returns at once unless k_advance has set finish_n.
+template <bool ALPHA>
+__global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool, QueueState* q,
+                                                int cur, long long* accum, uint32_t* nonfinite) {
+    const uint32_t n = q->finish_n;
+    if (n == 0) return;
+    const uint32_t* __restrict__ queue = pool.q_ext[cur];
+    const float inf = __int_as_float(0x7f800000);
+    unsigned long long rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[i];
+        Slot* sl = &pool.slot[slot];
+        bool cont = true;
+        while (cont) {
+            float4 o = sl->o, d = sl->d;
+            RngKey key{__float_as_uint(o.w), __float_as_uint(d.w), __float_as_uint(sl->thr.w), rp.seed};
+            HitRec h = traverse<false, ALPHA>(sc, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, 0.001f, inf, key, nullptr);
+            int32_t m = -1;
+            uint32_t kind = Q_MISS;
+            if (h.prim != kNone) {
+                m = hit_material(sc, h);
+                kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
+            }
+            sl->hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
+            shade_entry(sc, rp, pool, accum, nonfinite, kind, slot, cont);
+            ++rays;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
+    if (lane_id() == 0 && rays) atomicAdd(&q->rays, rays);
 }
 
 // PASS A (main.rs:166-222): Camera::albedo_normal (world.rs:81-93) at pixel centres
@@ -488,6 +563,8 @@ struct mrt_context {
     uint32_t w = 0, h = 0, count = 0;
     long long* d_accum = nullptr;
     uint32_t* d_nonfinite = nullptr;
+    float* d_sum_rgb = nullptr;  // staging for mrt_accum_download / mrt_resolve_rgb8 (allocated with the image: no malloc per call)
+    uint32_t* d_sum_b = nullptr;
     // pool
     Pool pool{};
     QueueState* d_q = nullptr;
@@ -498,6 +575,7 @@ struct mrt_context {
     bool opt_count = false, opt_time = false;
     uint64_t opt_pool_slots = 0;
     bool opt_shade_inorder = false;
+    uint32_t opt_finish_paths = 65536;
     uint32_t opt_refill_lanes = kRefillLanes, opt_node_lanes = kNodeLanes, opt_node_burst = 1;
     mrt_stats stats{};
     int grid_extend = 0, grid_extend_count = 0, grid_extend_slow = 0, grid_shade = 0, grid_generate = 0;
@@ -547,8 +625,12 @@ static void free_pool(mrt_context* ctx) {
 static void free_image(mrt_context* ctx) {
     cudaFree(ctx->d_accum);
     cudaFree(ctx->d_nonfinite);
+    cudaFree(ctx->d_sum_rgb);
+    cudaFree(ctx->d_sum_b);
     ctx->d_accum = nullptr;
     ctx->d_nonfinite = nullptr;
+    ctx->d_sum_rgb = nullptr;
+    ctx->d_sum_b = nullptr;
     ctx->w = ctx->h = ctx->count = 0;
 }
 
@@ -1017,7 +1099,7 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
-    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst};
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst, ctx->opt_finish_paths};
     if (ctx->scene.has_alpha) k_aov<true><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     else k_aov<false><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     AOV_TRY(cudaGetLastError());
@@ -1041,6 +1123,8 @@ int mrt_accum_reset(mrt_context* ctx, uint32_t w, uint32_t h) {
         free_image(ctx);
         MRT_CUDA(cudaMalloc(&ctx->d_accum, (size_t)w * h * 4 * sizeof(long long)));
         MRT_CUDA(cudaMalloc(&ctx->d_nonfinite, (size_t)w * h * sizeof(uint32_t)));
+        MRT_CUDA(cudaMalloc(&ctx->d_sum_rgb, (size_t)w * h * 3 * sizeof(float)));
+        MRT_CUDA(cudaMalloc(&ctx->d_sum_b, (size_t)w * h * sizeof(uint32_t)));
         ctx->w = w;
         ctx->h = h;
     }
@@ -1085,7 +1169,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     if ((rc = ensure_pool(ctx, total))) return rc;
     st.pool_slots = ctx->pool.slots;
     Pool pool = ctx->pool;
-    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst};
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst, ctx->opt_finish_paths};
 
     QueueState init;
     std::memset(&init, 0, sizeof init);
@@ -1106,7 +1190,12 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
             cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             if (ctx->opt_time)
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
-            k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q);
+            k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, rp.finish_paths);
+            if (rp.finish_paths) {
+                if (ctx->scene.has_alpha) k_finish<true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                else k_finish<false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                st.kernel_launches++;
+            }
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[0], ctx->stream));
             k_generate<<<ctx->grid_generate, 256, 0, ctx->stream>>>(ctx->cam, rp, pool, ctx->d_q, cur);
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[1], ctx->stream)); MRT_CUDA(cudaEventRecord(e[2], ctx->stream)); }
@@ -1173,18 +1262,11 @@ int mrt_accum_download(mrt_context* ctx, float* sum_rgb, uint32_t* sum_bounces, 
     if (!ctx->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
     MRT_CUDA(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)ctx->w * ctx->h;
-    float* d_rgb = nullptr;
-    uint32_t* d_b = nullptr;
-    MRT_CUDA(cudaMalloc(&d_rgb, npix * 12));
-    cudaError_t e = cudaMalloc(&d_b, npix * 4);
-    if (e != cudaSuccess) { cudaFree(d_rgb); return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e)); }
-    k_resolve_sums<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_accum, ctx->d_nonfinite, (uint32_t)npix, d_rgb, d_b);
-    if (sum_rgb) cudaMemcpyAsync(sum_rgb, d_rgb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream);
-    if (sum_bounces) cudaMemcpyAsync(sum_bounces, d_b, npix * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_rgb);
-    cudaFree(d_b);
-    if (e != cudaSuccess) return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e));
+    k_resolve_sums<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_accum, ctx->d_nonfinite, (uint32_t)npix, ctx->d_sum_rgb, ctx->d_sum_b);
+    MRT_CUDA(cudaGetLastError());
+    if (sum_rgb) MRT_CUDA(cudaMemcpyAsync(sum_rgb, ctx->d_sum_rgb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sum_bounces) MRT_CUDA(cudaMemcpyAsync(sum_bounces, ctx->d_sum_b, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MRT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (out_count) *out_count = ctx->count;
     return MRT_OK;
 }
@@ -1205,11 +1287,8 @@ int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8
     if (mode != 0 && mode != 1 && mode != 2) return fail(ctx, MRT_E_UNSUPPORTED, "only Default(0), Denoise(1, as Default) and Depth(2) are resolved on the device");
     MRT_CUDA(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)ctx->w * ctx->h;
-    uint8_t* d_out = nullptr;
-    uint32_t* d_max = nullptr;
-    MRT_CUDA(cudaMalloc(&d_out, npix * 3));
-    cudaError_t e = cudaMalloc(&d_max, 4);
-    if (e != cudaSuccess) { cudaFree(d_out); return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e)); }
+    uint8_t* d_out = reinterpret_cast<uint8_t*>(ctx->d_sum_rgb);  // staging buffers of the image, reused as byte output / max cell
+    uint32_t* d_max = ctx->d_sum_b;
     cudaMemsetAsync(d_max, 0, 4, ctx->stream);
     uint32_t h_max = 0;
     if (mode == 2) {
@@ -1219,9 +1298,7 @@ int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8
     }
     k_resolve_rgb8<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_accum, ctx->d_nonfinite, ctx->w, ctx->h, count, mode == 2 ? 2 : 0, flip, h_max, d_out);
     cudaMemcpyAsync(out, d_out, npix * 3, cudaMemcpyDeviceToHost, ctx->stream);
-    e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_out);
-    cudaFree(d_max);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(ctx, MRT_E_CUDA, cudaGetErrorString(e));
     return MRT_OK;
 }
@@ -1240,6 +1317,10 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             ctx->opt_refill_lanes = (uint32_t)value;
             return MRT_OK;
         case MRT_OPT_SHADE_INORDER: ctx->opt_shade_inorder = value != 0; return MRT_OK;
+        case MRT_OPT_FINISH_PATHS:
+            if (value > (1u << 22)) return fail(ctx, MRT_E_INVALID, "finish threshold out of range [0, 2^22]");
+            ctx->opt_finish_paths = (uint32_t)value;
+            return MRT_OK;
         case MRT_OPT_NODE_BURST:
             if (value < 1 || value > 64) return fail(ctx, MRT_E_INVALID, "burst out of range [1, 64]");
             ctx->opt_node_burst = (uint32_t)value;

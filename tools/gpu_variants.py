@@ -4,7 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.path.insert(0, ROOT)
     from mass_raytrace_b200 import NativeScene, Renderer, scenes
+    import tempfile
     work = {"cornell": (scenes.cornell_box(1.0), 1024, 1024, 16), "book1": (scenes.book1_spheres(1.5, 0.1), 1200, 800, 10)}
+    if os.environ.get("MRT_VAR_MESH"):
+        tmp = tempfile.mkdtemp(); n, md = scenes.write_synthetic_ply(os.path.join(tmp, "m.ply"), 1024, 512, seed=1)
+        work["mesh1m"] = (scenes.lucy_layout(os.path.join(tmp, "m.ply"), md, grid=0), 1920, 1080, 16)
     for name, ((w, c), W, H, spp) in work.items():
         r = Renderer(0); r.set_scene(NativeScene(w, c)); r.reset(W, H); r.accumulate(0, 2)
         r.set_option(Renderer.OPT_TIME_KERNELS, 1)
