@@ -34,6 +34,7 @@ WORKLOADS = {
     "cornell": (1, 1024, 1024, 1000, "Cornell box (reference scenes/cornell.rs: cube.ply instances, light, rotated block, glass sphere), 1024x1024, 1000 spp, max depth 50"),
     "mesh1m": (2, 1920, 1080, 256, "cube.ply + synthetic tessellated PLY mesh (1,048,576 triangles) under the triangle BVH, 1920x1080, 256 spp"),
     "book2": (3, 1920, 1080, 1000, "RTIOW book-2 final scene restated with reference parts (1024 box instances, volumes, image texture), 1920x1080, 1000 spp"),
+    "menger": (-1, 1920, 1080, 64, "extra (not a BASELINE config): Menger sponge of 160,000 cube instances (reference scenes/menger.rs at 4 levels), 1920x1080, 64 spp"),
     "mesh10m": (4, 3840, 2160, 4096, "10 synthetic meshes x 1,048,576 triangles, 3840x2160, 4096 spp split by spp across GPUs"),
 }
 
@@ -47,6 +48,8 @@ def build_workload(name, tmpdir):
         return scenes.cornell_box(1.0)
     if name == "book2":
         return scenes.book2_final()
+    if name == "menger":
+        return scenes.menger(levels=4)
     if name == "mesh1m":
         path = os.path.join(tmpdir, "mesh1m.ply")
         n, md = scenes.write_synthetic_ply(path, 1024, 512, seed=1)

@@ -50,6 +50,7 @@ void mrth_background_cubemap(mrth_scene*, const int surfaces6[6], float rx, floa
 int mrth_mesh_new(mrth_scene*, const float* verts, uint64_t n_tris, int tri_material);
 int mrth_mesh_new_uv(mrth_scene*, const float* verts, const float* normals, const float* uvs, uint64_t n_tris, int tri_material);
 int mrth_mesh_load_ply(mrth_scene*, const char* path, const int perm[3], int tri_material, float* max_abs);
+int mrth_mesh_load_stl(mrth_scene*, const char* path, const int perm[3], int tri_material); /* StlLoader::load_binary stl_loader.rs:10 */
 uint64_t mrth_mesh_tri_count(mrth_scene*, int mesh);
 void mrth_mesh_get_verts(mrth_scene*, int mesh, float* out9);
 uint64_t mrth_mesh_node_count(mrth_scene*, int mesh);

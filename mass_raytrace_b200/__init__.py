@@ -2,7 +2,7 @@
 mirror of the reference's scene API (api.py, libmrt_host.so). See DESIGN.md."""
 from .api import (ABSORB, BLEND_ADDITION, BLEND_DARKEN, BLEND_LIGHTEN, BLEND_SUBTRACTION, WRAP_CLAMP, WRAP_REPEAT, Camera, CubeMap, Dielectric,
                   DiffuseLight, FastRand, Instance, Lambertian, Metal, Mix, Model, MrtError, NativeScene, PlyLoader, Renderer, SkyBackground,
-                  SkySphere, SolidBackground, SolidColor, SolidColorFallback, Specular, Sphere, Texture, TextureBlend, Triangles, V3, V3_fill,
+                  SkySphere, SolidBackground, SolidColor, SolidColorFallback, Specular, Sphere, StlLoader, Texture, TextureBlend, Triangles, V3, V3_fill,
                   Volume, World, YCbCrTexture, render)
 from . import scenes  # noqa: F401
 

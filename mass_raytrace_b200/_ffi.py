@@ -110,6 +110,7 @@ def scene_api(prefix, with_desc):
         f"{p}_mesh_new": (C.c_int, [C.c_void_p, f32p, C.c_uint64, C.c_int]),
         f"{p}_mesh_new_uv": (C.c_int, [C.c_void_p, f32p, f32p, f32p, C.c_uint64, C.c_int]),
         f"{p}_mesh_load_ply": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int * 3), C.c_int, f32p]),
+        f"{p}_mesh_load_stl": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int * 3), C.c_int]),
         f"{p}_mesh_tri_count": (C.c_uint64, [C.c_void_p, C.c_int]),
         f"{p}_mesh_get_verts": (None, [C.c_void_p, C.c_int, f32p]),
         f"{p}_mesh_node_count": (C.c_uint64, [C.c_void_p, C.c_int]),

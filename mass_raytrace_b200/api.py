@@ -168,6 +168,7 @@ class Triangles:
     uvs: Optional[np.ndarray] = None
     ply_path: Optional[str] = None
     ply_perm: Tuple[int, int, int] = (0, 1, 2)
+    stl_path: Optional[str] = None
 
 
 class PlyLoader:
@@ -175,6 +176,13 @@ class PlyLoader:
     def load(path, vertex_perm=(0, 1, 2), material=ABSORB):
         """PlyLoader::load(path, |x,y,z| V3::new(v[perm]), |a,b,c| Triangle::new(material, a, b, c))  ply_loader.rs:273"""
         return Triangles(material=material, ply_path=str(path), ply_perm=tuple(vertex_perm))
+
+
+class StlLoader:
+    @staticmethod
+    def load_binary(path, vertex_perm=(0, 1, 2), material=ABSORB):
+        """StlLoader::load_binary(path, |x,y,z| V3::new(v[perm]), |a,b,c| Triangle::new(material, a, b, c))  stl_loader.rs:10"""
+        return Triangles(material=material, stl_path=str(path), ply_perm=tuple(vertex_perm))
 
 
 @dataclass(eq=False)
@@ -366,6 +374,10 @@ class NativeScene:
             h = self._fn("mesh_load_ply")(self._h, tris.ply_path.encode(), C.byref(perm), mat, C.byref(max_abs))
             self._check(h, f"PlyLoader.load({tris.ply_path})")
             self.mesh_max_abs[key] = max_abs.value
+        elif tris.stl_path is not None:
+            perm = (C.c_int * 3)(*tris.ply_perm)
+            h = self._fn("mesh_load_stl")(self._h, tris.stl_path.encode(), C.byref(perm), mat)
+            self._check(h, f"StlLoader.load_binary({tris.stl_path})")
         else:
             v = np.ascontiguousarray(tris.verts, dtype=np.float32).reshape(-1, 9)
             if tris.uvs is not None:

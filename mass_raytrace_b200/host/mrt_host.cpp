@@ -613,6 +613,33 @@ int mrth_mesh_load_ply(mrth_scene* s, const char* path, const int perm[3], int t
     if (!ply_read(path, perm, v, max_abs, s->err)) return MRT_E_INVALID;
     return mrth_mesh_new(s, v.data(), v.size() / 9, tri_material);
 }
+int mrth_mesh_load_stl(mrth_scene* s, const char* path, const int perm[3], int tri_material) {
+    // StlLoader::load_binary stl_loader.rs:10-66: header[80], u32 count, then per triangle {normal (ignored), a, b, c, u16 n, n attribute bytes}
+    if (!valid_material(s, tri_material, false)) return MRT_E_INVALID;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { s->err = std::string("cannot open ") + path; return MRT_E_INVALID; }
+    std::vector<float> v;
+    unsigned char header[80];
+    uint32_t count = 0;
+    bool ok = std::fread(header, 1, 80, f) == 80 && std::fread(&count, 4, 1, f) == 1;
+    for (uint32_t i = 0; ok && i < count; ++i) {
+        float rec[12];
+        uint16_t attr = 0;
+        ok = std::fread(rec, 4, 12, f) == 12 && std::fread(&attr, 2, 1, f) == 1;
+        if (ok && attr) ok = std::fseek(f, attr, SEEK_CUR) == 0;
+        if (ok)
+            for (int k = 0; k < 3; ++k)
+                for (int c = 0; c < 3; ++c) v.push_back(rec[3 + 3 * k + perm[c]]);
+    }
+    if (ok && count) {  // fseek past the end succeeds silently: make sure the last record was really there
+        long pos = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        ok = pos <= std::ftell(f);
+    }
+    std::fclose(f);
+    if (!ok) { s->err = "stl read error"; return MRT_E_INVALID; }
+    return mrth_mesh_new(s, v.data(), v.size() / 9, tri_material);
+}
 uint64_t mrth_mesh_tri_count(mrth_scene* s, int mesh) { return s->blas.at((size_t)mesh).n_tris; }
 void mrth_mesh_get_verts(mrth_scene* s, int mesh, float* out) {
     const mrt_blas& b = s->blas.at((size_t)mesh);

@@ -254,3 +254,30 @@ def book2_final(aspect_ratio=16.0 / 9.0, boxes_per_side=32, n_cluster=1000):
     world.build_bvh()
     look_from, look_at = V3(478, 278, -600), V3(278, 278, 0)
     return world, Camera(40.0, look_from, look_at, V3(0, 1, 0), aspect_ratio, 0.0, 10.0)
+
+
+MENGER_CUBE_SIDES = [(0, 1, 1), (1, 0, 1), (1, 1, 0), (0, -1, -1), (-1, 0, -1), (-1, -1, 0), (0, -1, 1), (-1, 0, 1), (-1, 1, 0), (0, 1, -1),
+                     (1, 0, -1), (1, -1, 0), (-1, -1, 1), (-1, 1, -1), (1, -1, -1), (-1, 1, 1), (1, -1, 1), (1, 1, -1), (1, 1, 1), (-1, -1, -1)]
+
+
+def menger(aspect_ratio=16.0 / 9.0, levels=5):
+    """Menger sponge of 20^levels unit-cube instances (reference src/scenes/menger.rs:29-124; levels = 5 there -> 3.2 M instances,
+    the TLAS stress case). The reference's nebula CubeMap needs un-shipped PNGs (eve.rs `environment`), so the sky is SkyBackground."""
+    world = World(SkyBackground())
+    cube = Model(PlyLoader.load(CUBE_PLY, material=ABSORB))
+    foggy = Metal(0.7, SolidColor((0.5, 0.5, 0.5, 1.0)))
+    material = Lambertian(SolidColor((1.0, 1.0, 1.0, 1.0)))
+    sides = np.array(MENGER_CUBE_SIDES, dtype=f32)
+    pos = np.zeros((1, 3), f32)
+    dims = f32(2.0)
+    for lvl in range(levels - 1, -1, -1):  # xyz = (i,j,k) * dims * 3^lvl + parent, coarsest level first (menger.rs:85-103)
+        step = sides * dims * f32(3.0) ** f32(lvl)
+        pos = (step[None, :, :] + pos[:, None, :]).reshape(-1, 3).astype(f32)
+    for p in pos:
+        world.add(cube.instance(V3(p[0], p[1], p[2]), V3(0, 0, 0), V3(1, 1, 1)).with_material(material))
+    extent = float(3.0 ** levels)
+    world.add(cube.instance(V3(0.0, -extent - 1.0, 0.0), V3(0, 0, 0), V3(500000.0, 1.0, 500000.0)).with_material(foggy))
+    world.build_bvh()
+    s = extent / 243.0  # the reference camera (2680, 140, 2000) frames the levels = 5 sponge (3^5 = 243)
+    look_from, look_at = V3(2680.0 * s, 140.0 * s, 2000.0 * s), V3(0, 0, 0)
+    return world, Camera(15.0, look_from, look_at, V3(0, 1, 0), aspect_ratio, 0.0, _length(look_from))

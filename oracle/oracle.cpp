@@ -1099,6 +1099,33 @@ static bool ply_load(const std::string& path, const int perm[3], std::vector<V3>
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// stl_loader.rs:10-66 — binary STL: 80-byte header, u32 count, per triangle 12 floats (normal ignored) + u16 attribute byte count
+// ---------------------------------------------------------------------------------------------
+static bool stl_load_binary(const std::string& path, const int perm[3], std::vector<V3>& tri_verts, std::string& err) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { err = "cannot open " + path; return false; }
+    char header[80];
+    if (!in.read(header, 80)) { err = "stl read error"; return false; }
+    uint32_t tri_count = 0;
+    if (!in.read((char*)&tri_count, 4)) { err = "stl read error"; return false; }
+    for (uint32_t i = 0; i < tri_count; ++i) {
+        float f[12];
+        if (!in.read((char*)f, 48)) { err = "stl read error"; return false; }
+        for (int k = 0; k < 3; ++k) {
+            const float* v = f + 3 + 3 * k;
+            tri_verts.push_back({v[perm[0]], v[perm[1]], v[perm[2]]});
+        }
+        uint16_t attr = 0;
+        if (!in.read((char*)&attr, 2)) { err = "stl read error"; return false; }
+        if (attr) {
+            std::vector<char> skip(attr);
+            if (!in.read(skip.data(), attr)) { err = "stl read error"; return false; }
+        }
+    }
+    return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1212,6 +1239,15 @@ int orc_mesh_new_uv(orc_scene* s, const float* v, const float* nn, const float* 
 int orc_mesh_load_ply(orc_scene* s, const char* path, const int perm[3], int tri_material, float* max_abs) {
     std::vector<V3> tv;
     if (!ply_load(path, perm, tv, max_abs, s->err)) return -1;
+    Mesh* m = new Mesh();
+    const Material* tm = mat(s, tri_material);
+    m->tris.reserve(tv.size() / 3);
+    for (size_t i = 0; i + 2 < tv.size(); i += 3) m->tris.emplace_back(tm, tv[i], tv[i + 1], tv[i + 2]);
+    return finish_mesh(s, m);
+}
+int orc_mesh_load_stl(orc_scene* s, const char* path, const int perm[3], int tri_material) {
+    std::vector<V3> tv;
+    if (!stl_load_binary(path, perm, tv, s->err)) return -1;
     Mesh* m = new Mesh();
     const Material* tm = mat(s, tri_material);
     m->tris.reserve(tv.size() / 3);

@@ -73,6 +73,8 @@ int orc_mesh_new_uv(orc_scene*, const float* verts, const float* normals, const 
 /* PlyLoader::load(path, |x,y,z| V3(v[perm0],v[perm1],v[perm2]), |a,b,c| Triangle::new(material,a,b,c)) ply_loader.rs:273
    max_abs (nullable) receives max(|x|,|y|,|z|) over vertices (scenes/lucy.rs:37). Returns mesh handle or <0. */
 int orc_mesh_load_ply(orc_scene*, const char* path, const int perm[3], int tri_material, float* max_abs);
+/* StlLoader::load_binary(path, |x,y,z| V3(v[perm]), |a,b,c| Triangle::new(material,a,b,c)) stl_loader.rs:10 */
+int orc_mesh_load_stl(orc_scene*, const char* path, const int perm[3], int tri_material);
 uint64_t orc_mesh_tri_count(orc_scene*, int mesh);
 void orc_mesh_get_verts(orc_scene*, int mesh, float* out9);            /* 9 floats per triangle */
 uint64_t orc_mesh_node_count(orc_scene*, int mesh);                    /* BvhNode count of the BLAS */

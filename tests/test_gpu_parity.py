@@ -146,6 +146,18 @@ def test_aov_book2_with_uv_mesh_texture_and_volumes(renderer, keep_topology):
         assert abs(fg - fo) < 0.01 + 0.15 * fo, (vid, fg, fo)
 
 
+def test_aov_menger_sponge_instances(renderer):
+    """scenes/menger.rs at 3 levels: 8,000 unit-cube instances of one 12-triangle BLAS under the TLAS."""
+    world, camera = scenes.menger(levels=3)
+    assert len(world.objects) == 8001
+    renderer.set_scene(NativeScene(world, camera))
+    g = renderer.render_aov(480, 270)
+    o = OracleScene(world, camera).render_aov(480, 270)
+    check_aov(g, o, albedo_exact=False, max_ties=int(0.03 * 480 * 270))  # axis-aligned unit cubes on an integer lattice: many pixel-exact edges
+    assert len(np.unique(g["object"])) > 500
+    stat_compare(renderer, world, camera, 96, 54, 32)
+
+
 def test_aov_world_without_bvh(renderer):
     # World::intersect before build_bvh: linear closest hit over the object list (world.rs:131-144); > 8 roots uses the list path
     for n_spheres in (5, 14):

@@ -106,3 +106,40 @@ def test_truncated_and_out_of_range(tmp_path, backend):
         _load(p, backend)
     with pytest.raises(RuntimeError, match="cannot open"):
         _load(str(tmp_path / "missing.ply"), backend)
+
+
+# ---- StlLoader (reference src/stl_loader.rs:10-66) --------------------------------------------------------------------------
+def _load_stl(path, backend, perm=(0, 1, 2)):
+    from mass_raytrace_b200 import StlLoader
+
+    w = World(SolidBackground(V3(0, 0, 0)))
+    t = StlLoader.load_binary(path, vertex_perm=perm)
+    w.add(Model(t))
+    return backend(w).mesh_verts(t)
+
+
+def _write_stl(path, tris, attr_bytes=0, truncate=0):
+    data = b"binary stl written by the tests".ljust(80, b"\0") + struct.pack("<I", len(tris))
+    for k, t in enumerate(tris):
+        data += struct.pack("<3f", 0.0, 0.0, 1.0) + struct.pack("<9f", *t)
+        n = attr_bytes if k % 2 == 0 else 0
+        data += struct.pack("<H", n) + b"\xAB" * n  # the attribute count is a BYTE count that the loader skips (:58-61)
+    with open(path, "wb") as f:
+        f.write(data[:len(data) - truncate] if truncate else data)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_stl_binary(tmp_path, backend):
+    p = str(tmp_path / "m.stl")
+    tris = [[0, 0, 0, 1, 0, 0, 0, 1, 0], [0, 0, 1, 2, 0, 1, 0, 3, 1], [5, 6, 7, 8, 9, 10, 11, 12, 14]]
+    _write_stl(p, tris)
+    assert _load_stl(p, backend).tolist() == tris
+    _write_stl(p, tris, attr_bytes=6)  # non-zero attribute blocks are skipped
+    assert _load_stl(p, backend).tolist() == tris
+    assert _load_stl(p, backend, perm=(1, 2, 0))[2].tolist() == [6, 7, 5, 9, 10, 8, 12, 14, 11]
+    _write_stl(p, tris, truncate=10)
+    with pytest.raises(RuntimeError, match="read error"):
+        _load_stl(p, backend)
+    _write_stl(p, [])
+    with pytest.raises(RuntimeError):  # Model::new over an empty Vec: BvhNode::new hits unreachable!() (geom.rs:153)
+        _load_stl(p, backend)
