@@ -219,7 +219,6 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     r = Renderer(local_rank, stream=stream.cuda_stream)
     r.set_scene(host)
-    r.set_option(Renderer.OPT_TIME_KERNELS, 1)
     npix = w * h
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -272,9 +271,23 @@ def main():
     value = paths / total_s / 1e6
 
     # ---- roofline of the dominant kernel (extend): algorithmic bytes per launch / mean launch duration ----------
-    ext_ms = sum(s["extend_ms"] for s in stats)
-    ext_launches = sum(s["iterations"] for s in stats)  # launches that had rays (the speculative tail launches exit at once)
-    rays_local = sum(s["rays"] for s in stats)
+    # Two more steps of the same workload with a CUDA-event pair around every generate / extend / shade launch on the render
+    # stream. They are kept out of the steps that produce `value` because ~6 event records per wavefront iteration cost ~2-3 %.
+    r.set_option(Renderer.OPT_TIME_KERNELS, 1)
+    tstats, tstep_ms = [], []
+    for i in range(2):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        tstats.append(step(args.warmup + args.steps + i))
+        e1.record(stream)
+        barrier()
+        tstep_ms.append(e0.elapsed_time(e1))
+    ext_ms = sum(s["extend_ms"] for s in tstats)
+    ext_launches = sum(s["iterations"] for s in tstats)  # launches that had rays (the speculative tail launches exit at once)
+    rays_local = sum(s["rays"] for s in tstats)
     r.set_option(Renderer.OPT_TIME_KERNELS, 0)
     r.set_option(Renderer.OPT_COUNT_VISITS, 1)
     with torch.cuda.stream(stream):
@@ -296,8 +309,9 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "alg_bytes_per_ray": b_ray, "per_ray": per_ray, "rays_per_launch": rays_local / max(ext_launches, 1),
-                "mean_launch_ms": ext_ms / max(ext_launches, 1), "extend_share_of_step": ext_ms / sum(step_ms),
-                "shade_share_of_step": sum(s["shade_ms"] for s in stats) / sum(step_ms),
+                "mean_launch_ms": ext_ms / max(ext_launches, 1), "extend_share_of_step": ext_ms / sum(tstep_ms),
+                "shade_share_of_step": sum(s["shade_ms"] for s in tstats) / sum(tstep_ms),
+                "generate_share_of_step": sum(s["generate_ms"] for s in tstats) / sum(tstep_ms),
                 "note": "algorithmic bytes are served mostly by L1/L2 when the acceleration structure is cache-resident, so achieved can exceed the HBM peak"}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------------
