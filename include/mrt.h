@@ -261,10 +261,10 @@ enum {
     MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */
     MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
     MRT_OPT_POOL_SLOTS = 3,   /* path-state slots (0 = default 2^22) */
-    MRT_OPT_REFILL_LANES = 4, /* k_extend: refill finished lanes when at least this many of a warp's 32 are idle */
-    MRT_OPT_NODE_LANES = 5,   /* k_extend: run a node-visit phase when at least this many lanes are at an inner node; 0 = no voting (chain mode) */
-    MRT_OPT_NODE_BURST = 6,   /* k_extend: node visits per lane per node phase */
+    MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes once at least this many of a warp's 32 lanes are idle (default 32: whole batches) */
     MRT_OPT_SHADE_INORDER = 7, /* measurement aid: shade in slot order instead of through the material-sorted queues (slower) */
+    MRT_OPT_BVH_LEAF_TRIS = 9, /* SAH rebuild at the next mrt_scene_upload: most triangles per BLAS leaf, 1..4 (default 4) */
+    MRT_OPT_BVH_TRI_COST = 10, /* SAH rebuild: cost of one triangle test in hundredths of a node visit (default 100) */
     MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 65536, 0 = off) */
 };
 int mrt_set_option(mrt_context* ctx, int option, uint64_t value);

@@ -27,6 +27,7 @@ float mrth_rand_f32(mrth_scene*);           /* f32::rand() math.rs:244 for scene
 /* texture.rs */
 int mrth_surface_solid(mrth_scene*, float r, float g, float b, float a);
 int mrth_surface_texture(mrth_scene*, const uint8_t* rgba, uint32_t w, uint32_t h, int wrap); /* Texture::load_bytes :70 */
+int mrth_surface_texture_png(mrth_scene*, const char* path, int wrap); /* Texture::load_png :29 — 8-bit PNG, decoded by the library itself */
 int mrth_surface_ycbcr(mrth_scene*, int luma_tex, int chroma_tex);
 int mrth_surface_blend(mrth_scene*, int mode, int left, int right);
 int mrth_surface_fallback(mrth_scene*, float r, float g, float b, float a, int inner);
@@ -51,9 +52,18 @@ int mrth_mesh_new(mrth_scene*, const float* verts, uint64_t n_tris, int tri_mate
 int mrth_mesh_new_uv(mrth_scene*, const float* verts, const float* normals, const float* uvs, uint64_t n_tris, int tri_material);
 int mrth_mesh_load_ply(mrth_scene*, const char* path, const int perm[3], int tri_material, float* max_abs);
 int mrth_mesh_load_stl(mrth_scene*, const char* path, const int perm[3], int tri_material); /* StlLoader::load_binary stl_loader.rs:10 */
+/* ObjLoader::load(path, SimpleTexturedBuilder::with_filter(wrap, groups)) obj_loader.rs:160-308, :332 — `v/vt/vn` faces (first three
+   corners), `usemtl` + `mtllib` with `Kd` / `map_Kd` -> one Lambertian per MTL material, v -> 1 - v; filtered_groups: newline-separated
+   `o`/`g` names whose faces are skipped, or NULL */
+int mrth_mesh_load_obj(mrth_scene*, const char* path, int wrap, const char* filtered_groups);
+/* ObjLoader::load(path, obj_fns(V3::new, V3::new, V2::new, |a, b, c| Triangle::with_norms_and_uvs(material, a, b, c))) obj_loader.rs:45 (eve.rs:330) */
+int mrth_mesh_load_obj_with(mrth_scene*, const char* path, int tri_material);
 uint64_t mrth_mesh_tri_count(mrth_scene*, int mesh);
 void mrth_mesh_get_verts(mrth_scene*, int mesh, float* out9);
 uint64_t mrth_mesh_node_count(mrth_scene*, int mesh);
+void mrth_mesh_get_shading(mrth_scene*, int mesh, float* normals9, float* uvs6, int32_t* materials); /* per triangle; any pointer may be NULL */
+/* returns the material kind (MRT_MAT_*); colour of a SolidColor surface, or size + FNV-1a hash of the f32 texels of a Texture surface */
+int mrth_material_info(mrth_scene*, int material, float color4[4], uint32_t wh[2], uint64_t* texel_hash);
 
 int mrth_add_sphere(mrth_scene*, int material, float cx, float cy, float cz, float radius);
 int mrth_add_model(mrth_scene*, int mesh, int override_material);

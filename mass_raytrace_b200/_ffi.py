@@ -92,6 +92,7 @@ def scene_api(prefix, with_desc):
         f"{p}_rand_f32": (C.c_float, [C.c_void_p]),
         f"{p}_surface_solid": (C.c_int, [C.c_void_p] + [C.c_float] * 4),
         f"{p}_surface_texture": (C.c_int, [C.c_void_p, u8p, C.c_uint32, C.c_uint32, C.c_int]),
+        f"{p}_surface_texture_png": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
         f"{p}_surface_ycbcr": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
         f"{p}_surface_blend": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
         f"{p}_surface_fallback": (C.c_int, [C.c_void_p] + [C.c_float] * 4 + [C.c_int]),
@@ -111,6 +112,10 @@ def scene_api(prefix, with_desc):
         f"{p}_mesh_new_uv": (C.c_int, [C.c_void_p, f32p, f32p, f32p, C.c_uint64, C.c_int]),
         f"{p}_mesh_load_ply": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int * 3), C.c_int, f32p]),
         f"{p}_mesh_load_stl": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int * 3), C.c_int]),
+        f"{p}_mesh_load_obj": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p]),
+        f"{p}_mesh_load_obj_with": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+        f"{p}_mesh_get_shading": (None, [C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_int32)]),
+        f"{p}_material_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 4), C.POINTER(C.c_uint32 * 2), C.POINTER(C.c_uint64)]),
         f"{p}_mesh_tri_count": (C.c_uint64, [C.c_void_p, C.c_int]),
         f"{p}_mesh_get_verts": (None, [C.c_void_p, C.c_int, f32p]),
         f"{p}_mesh_node_count": (C.c_uint64, [C.c_void_p, C.c_int]),

@@ -74,6 +74,12 @@ class Texture:  # texture.rs:21
 
 
 @dataclass(eq=False)
+class TextureFile:  # Texture::load_png(path, wrapping) texture.rs:29, decoded natively by the scene builder
+    path: str
+    wrapping: int = WRAP_REPEAT
+
+
+@dataclass(eq=False)
 class YCbCrTexture:  # texture.rs:207
     luma: Texture
     chroma: Texture
@@ -169,6 +175,8 @@ class Triangles:
     ply_path: Optional[str] = None
     ply_perm: Tuple[int, int, int] = (0, 1, 2)
     stl_path: Optional[str] = None
+    obj_path: Optional[str] = None
+    obj_builder: object = None
 
 
 class PlyLoader:
@@ -183,6 +191,31 @@ class StlLoader:
     def load_binary(path, vertex_perm=(0, 1, 2), material=ABSORB):
         """StlLoader::load_binary(path, |x,y,z| V3::new(v[perm]), |a,b,c| Triangle::new(material, a, b, c))  stl_loader.rs:10"""
         return Triangles(material=material, stl_path=str(path), ply_perm=tuple(vertex_perm))
+
+
+@dataclass(eq=False)
+class SimpleTexturedBuilder:  # obj_loader.rs:160: SimpleTexturedBuilder::new(wrapping) / ::with_filter(wrapping, filtered_groups)
+    wrapping: int = WRAP_REPEAT
+    filtered_groups: Tuple[str, ...] = ()
+
+    @staticmethod
+    def with_filter(wrapping, filtered_groups):
+        return SimpleTexturedBuilder(wrapping, tuple(filtered_groups))
+
+
+@dataclass(eq=False)
+class ObjFns:  # obj_fns(V3::new, V3::new, V2::new, |a, b, c| Triangle::with_norms_and_uvs(material, a, b, c))  obj_loader.rs:45, eve.rs:330
+    material: object = ABSORB
+
+
+class ObjLoader:
+    @staticmethod
+    def load(path, builder):
+        """ObjLoader::load(path, builder) obj_loader.rs:332 -> Vec<Triangle<..>> (parsed natively by each backend)"""
+        if not isinstance(builder, (SimpleTexturedBuilder, ObjFns)):
+            raise TypeError("builder must be SimpleTexturedBuilder or ObjFns")
+        material = builder.material if isinstance(builder, ObjFns) else ABSORB
+        return Triangles(material=material, obj_path=str(path), obj_builder=builder)
 
 
 @dataclass(eq=False)
@@ -314,6 +347,9 @@ class NativeScene:
         elif isinstance(s, Texture):
             arr = np.ascontiguousarray(s.rgba, dtype=np.uint8)
             h = self._fn("surface_texture")(self._h, arr.ctypes.data_as(_ffi.u8p), arr.shape[1], arr.shape[0], s.wrapping)
+        elif isinstance(s, TextureFile):
+            self._prepare_png(s.path)
+            h = self._fn("surface_texture_png")(self._h, s.path.encode(), s.wrapping)
         elif isinstance(s, YCbCrTexture):
             h = self._fn("surface_ycbcr")(self._h, self._surface(s.luma), self._surface(s.chroma))
         elif isinstance(s, TextureBlend):
@@ -363,12 +399,27 @@ class NativeScene:
         else:
             raise TypeError(f"unsupported background {type(b).__name__}")
 
+    def _prepare_png(self, path):
+        """Hook for backends that do not decode PNG themselves (the tests' CPU checker); the product library does."""
+
+    def _prepare_obj(self, path):
+        """Same hook for the PNG files an OBJ's material library may name."""
+
     def mesh(self, tris: Triangles):
         key = id(tris)
         if key in self._mesh:
             return self._mesh[key]
         mat = self._material(tris.material)
-        if tris.ply_path is not None:
+        if tris.obj_path is not None:
+            self._prepare_obj(tris.obj_path)
+            b = tris.obj_builder
+            if isinstance(b, SimpleTexturedBuilder):
+                groups = "\n".join(b.filtered_groups).encode() if b.filtered_groups else None
+                h = self._fn("mesh_load_obj")(self._h, tris.obj_path.encode(), b.wrapping, groups)
+            else:
+                h = self._fn("mesh_load_obj_with")(self._h, tris.obj_path.encode(), mat)
+            self._check(h, f"ObjLoader.load({tris.obj_path})")
+        elif tris.ply_path is not None:
             perm = (C.c_int * 3)(*tris.ply_perm)
             max_abs = C.c_float(0)
             h = self._fn("mesh_load_ply")(self._h, tris.ply_path.encode(), C.byref(perm), mat, C.byref(max_abs))
@@ -429,6 +480,20 @@ class NativeScene:
         self._fn("mesh_get_verts")(self._h, m, out.ctypes.data_as(_ffi.f32p))
         return out
 
+    def mesh_shading(self, tris: Triangles):
+        """Per-triangle vertex normals (n, 9), uvs (n, 6) and material handles (n,) of a mesh."""
+        m = self.mesh(tris)
+        n = self._fn("mesh_tri_count")(self._h, m)
+        nrm, uv, mat = np.zeros((n, 9), np.float32), np.zeros((n, 6), np.float32), np.zeros(n, np.int32)
+        self._fn("mesh_get_shading")(self._h, m, nrm.ctypes.data_as(_ffi.f32p), uv.ctypes.data_as(_ffi.f32p), mat.ctypes.data_as(C.POINTER(C.c_int32)))
+        return nrm, uv, mat
+
+    def material_info(self, material):
+        """(kind, colour of a SolidColor surface, (w, h) and texel hash of a Texture surface) of a material handle."""
+        color, wh, hsh = (C.c_float * 4)(), (C.c_uint32 * 2)(), C.c_uint64(0)
+        kind = self._fn("material_info")(self._h, int(material), color, wh, C.byref(hsh))
+        return kind, tuple(color), tuple(wh), hsh.value
+
     def mesh_node_count(self, tris: Triangles):
         return self._fn("mesh_node_count")(self._h, self.mesh(tris))
 
@@ -450,7 +515,8 @@ class MrtError(RuntimeError):
 class Renderer:
     """One GPU behind the C ABI of include/mrt.h. Replaces render() (main.rs:150-295); no CPU fallback."""
 
-    OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_POOL_SLOTS, OPT_REFILL_LANES, OPT_NODE_LANES, OPT_NODE_BURST, OPT_SHADE_INORDER, OPT_FINISH_PATHS = 1, 2, 3, 4, 5, 6, 7, 8
+    OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_POOL_SLOTS, OPT_REFILL_LANES, OPT_SHADE_INORDER, OPT_FINISH_PATHS = 1, 2, 3, 4, 7, 8
+    OPT_BVH_LEAF_TRIS, OPT_BVH_TRI_COST = 9, 10
 
     def __init__(self, device=0, stream=None):
         self.lib = _ffi.cuda_lib()

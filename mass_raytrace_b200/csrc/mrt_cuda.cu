@@ -49,7 +49,7 @@ struct QueueState {
 struct RenderParams {
     uint32_t w, h, npix, spp_begin, max_depth;
     uint2 seed;
-    uint32_t refill_lanes, node_lanes, node_burst;  // warp-vote thresholds of k_extend
+    uint32_t refill_lanes;                          // k_extend hands rays to idle lanes once this many lanes of a warp are idle
     uint32_t finish_paths;                          // drain threshold of k_finish (0 = never)
 };
 
@@ -159,29 +159,36 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
     }
 }
 
-// Persistent lanes. Every thread keeps one traversal in flight; when at least `refill_lanes` lanes of a warp have finished, the
-// warp commits their hits (hit record + material-sorted shade queue, one atomic per warp and kind) and refills those lanes from
-// the ray queue with one atomic. Between refills each lane descends to its next leaf and tests it ("chain mode", node_lanes = 0).
-// A second scheduling mode (node_lanes > 0) makes the warp vote each iteration and run either one node visit or the pending
-// primitive tests with all lanes that want that kind of work; it raises the active lanes per instruction (8 -> 15 of 32 on the
-// Cornell box) but its per-iteration voting overhead cancels the gain on B200 (profiles/README.md), so chain mode is the default.
-constexpr uint32_t kRefillLanes = 24;  // defaults; MRT_OPT_REFILL_LANES / MRT_OPT_NODE_LANES / MRT_OPT_NODE_BURST override them
-constexpr uint32_t kNodeLanes = 0;
+// Persistent warps. Every thread keeps one traversal in flight and, between refills, descends to its next leaf and tests it
+// ("chain": all lanes run the node loop together, then the leaf code of each primitive kind present). When at least
+// `refill_lanes` lanes of a warp have finished, the warp commits their hits -- hit record, then one __match_any_sync + one
+// atomicAdd per (warp, material kind) to append to the material-sorted shade queues -- and refills those lanes with one
+// atomicAdd on the queue cursor. Measured on B200 (profiles/README.md): the best threshold is 32, i.e. a warp takes 32
+// consecutive queue entries, runs them to the end and commits them together. Consecutive entries are neighbouring pixels or
+// paths shaded together, so they start in phase (all at the root, then all a few nodes from their next leaf); refilling single
+// lanes early -- even for the price of a few shared-memory loads from a prefetched ring -- mixes rays that need five node
+// visits with rays that need one and costs more warp instructions than the idle lanes save.
+// Leaving an instance is free: stack entries pushed before the instance was entered lie below inst_base, and popping one
+// restores the world-space ray from shared memory (no sentinel entries).
+constexpr uint32_t kRefillLanes = 32;  // default; MRT_OPT_REFILL_LANES overrides it
+constexpr int kExtendThreads = 128;
 
-template <bool COUNT, bool ALPHA>
-__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
-                                                QueueState* q, int cur) {
+template <bool COUNT, bool SLOW>
+__global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
+                                                                                 QueueState* q, int cur) {
+    __shared__ float s_world[6 * kExtendThreads];  // world-space rays, needed again when a lane leaves an instance (keeps 6 registers free)
+    WorldRayShared<kExtendThreads> ws{&s_world[threadIdx.x]};
     const uint32_t n = q->n_ext;
     const uint32_t* __restrict__ queue = pool.q_ext[cur];
     const float inf = __int_as_float(0x7f800000);
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t refill_lanes = rp.refill_lanes;
     VisitCounters cnt{0, 0, 0, 0, 0};
     uint32_t stack[kStackSize];
     Traversal T;
     T.sp = 0;
     T.inst_base = 0;
-    T.linear_next = 0;
     T.ref = kNone;
     T.best = HitRec{inf, kNone, kNone};
     RngKey key{0u, 0u, 0u, rp.seed};
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene s
     bool active = false, pending = false, drained = false;
     for (;;) {
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle == 0xffffffffu || (!drained && (uint32_t)__popc(idle) >= rp.refill_lanes)) {
+        if (idle == 0xffffffffu || (!drained && (uint32_t)__popc(idle) >= refill_lanes)) {
             // ---- commit finished rays: world.rs:68 result -> hit record, shade queue by material kind -----------
             uint32_t kind = 0xFFu;
             if (pending) {
@@ -224,38 +231,25 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DScene s
                     slot = queue[i];
                     const Slot* sl = &pool.slot[slot];
                     float4 o = sl->o, d = sl->d;
-                    key.pixel = __float_as_uint(o.w);
-                    key.sample = __float_as_uint(d.w);
-                    if (sc.n_volumes) key.bounce = __float_as_uint(sl->thr.w);
-                    trav_begin(sc, T, stack, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, inf);  // world.rs:68: [0.001, +inf)
+                    if (SLOW) {
+                        key.pixel = __float_as_uint(o.w);
+                        key.sample = __float_as_uint(d.w);
+                        key.bounce = __float_as_uint(sl->thr.w);
+                    }
+                    trav_begin(sc, T, ws, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, inf);  // world.rs:68: [0.001, +inf)
                     active = true;
                 }
                 drained = base + want >= n;
             }
             if (__ballot_sync(0xffffffffu, active) == 0) break;
         }
-        if (active && T.ref == kNone && !trav_pop(sc, T, stack)) {
+        if (active && T.ref == kNone && !trav_pop(T, stack, ws)) {
             active = false;
             pending = true;
         }
-        if (rp.node_lanes == 0) {  // chain mode: each lane descends to its next leaf and tests it before the warp votes again
-            if (active) {
-                while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
-                if (T.ref != kNone) trav_leaf<COUNT, ALPHA>(sc, T, stack, 0.001f, key, &cnt);
-            }
-            continue;
-        }
-        const bool at_node = active && ref_is_node(T.ref);
-        const bool at_leaf = active && !at_node;
-        const uint32_t nodes = __ballot_sync(0xffffffffu, at_node);
-        const uint32_t leaves = __ballot_sync(0xffffffffu, at_leaf);
-        if ((uint32_t)__popc(nodes) >= rp.node_lanes || leaves == 0) {
-            if (at_node) {
-                trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
-                for (uint32_t b = 1; b < rp.node_burst && ref_is_node(T.ref); ++b) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
-            }
-        } else {
-            if (at_leaf) trav_leaf<COUNT, ALPHA>(sc, T, stack, 0.001f, key, &cnt);
+        if (active) {
+            while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
+            if (T.ref != kNone) trav_leaf<COUNT, SLOW>(sc, T, stack, ws, 0.001f, key, &cnt);
         }
     }
     if (COUNT) {
@@ -406,7 +400,7 @@ __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade_ino
 
 // Drain: one thread per remaining path, each looping extend + shade until its path ends (paths are independent, so no
 // grid-wide step is needed). Launched every iteration; returns at once unless k_advance has set finish_n.
-template <bool ALPHA>
+template <bool SLOW>
 __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool, QueueState* q,
                                                 int cur, long long* accum, uint32_t* nonfinite) {
     const uint32_t n = q->finish_n;
@@ -421,7 +415,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene s
         while (cont) {
             float4 o = sl->o, d = sl->d;
             RngKey key{__float_as_uint(o.w), __float_as_uint(d.w), __float_as_uint(sl->thr.w), rp.seed};
-            HitRec h = traverse<false, ALPHA>(sc, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, 0.001f, inf, key, nullptr);
+            HitRec h = traverse<false, SLOW>(sc, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, 0.001f, inf, key, nullptr);
             int32_t m = -1;
             uint32_t kind = Q_MISS;
             if (h.prim != kNone) {
@@ -438,7 +432,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene s
 }
 
 // PASS A (main.rs:166-222): Camera::albedo_normal (world.rs:81-93) at pixel centres
-template <bool ALPHA>
+template <bool SLOW>
 __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp,
                                              float* albedo, float* normal, uint32_t* object_id, uint32_t* tri_id, float* t_out) {
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,7 +440,7 @@ __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, 
     const float inf = __int_as_float(0x7f800000);
     Ray ray = camera_ray(cam, rp, pixel, 0u, false);
     RngKey key{pixel, 0u, 0u, rp.seed};
-    HitRec h = traverse<false, ALPHA>(sc, ray, 0.001f, inf, key, nullptr);
+    HitRec h = traverse<false, SLOW>(sc, ray, 0.001f, inf, key, nullptr);
     V3 a, n{0.0f, 0.0f, 0.0f};
     uint32_t obj = kNone, tri = kNone;
     float t = inf;
@@ -576,7 +570,8 @@ struct mrt_context {
     uint64_t opt_pool_slots = 0;
     bool opt_shade_inorder = false;
     uint32_t opt_finish_paths = 65536;
-    uint32_t opt_refill_lanes = kRefillLanes, opt_node_lanes = kNodeLanes, opt_node_burst = 1;
+    uint32_t opt_leaf_tris = 4, opt_tri_cost = 100;
+    uint32_t opt_refill_lanes = kRefillLanes;
     mrt_stats stats{};
     int grid_extend = 0, grid_extend_count = 0, grid_extend_slow = 0, grid_shade = 0, grid_generate = 0;
 };
@@ -852,7 +847,7 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         if (d < 0) return fail(ctx, MRT_E_INVALID, why);
         tlas_depth = std::max(tlas_depth, d);
     }
-    if (tlas_depth + blas_depth + 2 + (int)std::min<uint32_t>(s->n_roots, 8) > kStackSize)
+    if (tlas_depth + blas_depth + 2 > kStackSize)
         return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack");
 
     // ---- acceleration structure: the caller's topology re-laid out, or (default) a SAH rebuild -----------------------------
@@ -879,6 +874,7 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     };
     const float empty_lo[3] = {inf, inf, inf}, empty_hi[3] = {-inf, -inf, -inf};
     int max_tlas_depth = tlas_depth, max_blas_depth = blas_depth;
+    uint32_t device_root = kNone;  // stays kNone for an empty world
     if (keep) {
         nodes.resize(s->n_nodes);
         for (uint64_t i = 0; i < s->n_nodes; ++i) {
@@ -893,6 +889,48 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         }
         for (uint64_t i = 0; i < s->n_tris; ++i) tri_map[i] = (uint32_t)i;
         for (uint64_t i = 0; i < s->n_blas; ++i) blas_root[i] = s->blas[i].root;
+        if (s->n_roots == 1) {
+            device_root = roots[0];
+            if (MRT_REF_KIND(device_root) != MRT_PRIM_NODE) {  // a lone primitive still needs a node to hold its box
+                float lo[3], hi[3];
+                leaf_bounds(s, device_root, lo, hi);
+                DNode o{};
+                set_child(o, 0, device_root, lo, hi);
+                set_child(o, 1, kNone, empty_lo, empty_hi);
+                nodes.push_back(o);
+                device_root = MRT_REF(MRT_PRIM_NODE, (uint32_t)nodes.size() - 1);
+            }
+        } else if (s->n_roots > 1) {
+            // a plain object list (World::intersect's loop, world.rs:135-140) has no topology to keep: a balanced tree over the
+            // entries in list order visits the same objects; each entry keeps its own subtree as the caller built it
+            struct Item { uint32_t ref; float lo[3], hi[3]; };
+            std::vector<Item> level(s->n_roots);
+            for (uint32_t i = 0; i < s->n_roots; ++i) { level[i].ref = roots[i]; leaf_bounds(s, roots[i], level[i].lo, level[i].hi); }
+            int extra = 0;
+            while (level.size() > 1) {
+                std::vector<Item> next;
+                for (size_t i = 0; i < level.size(); i += 2) {
+                    DNode o{};
+                    Item it;
+                    set_child(o, 0, level[i].ref, level[i].lo, level[i].hi);
+                    if (i + 1 < level.size()) {
+                        set_child(o, 1, level[i + 1].ref, level[i + 1].lo, level[i + 1].hi);
+                        for (int k = 0; k < 3; ++k) { it.lo[k] = std::fmin(level[i].lo[k], level[i + 1].lo[k]); it.hi[k] = std::fmax(level[i].hi[k], level[i + 1].hi[k]); }
+                    } else {
+                        set_child(o, 1, kNone, empty_lo, empty_hi);
+                        for (int k = 0; k < 3; ++k) { it.lo[k] = level[i].lo[k]; it.hi[k] = level[i].hi[k]; }
+                    }
+                    nodes.push_back(o);
+                    it.ref = MRT_REF(MRT_PRIM_NODE, (uint32_t)nodes.size() - 1);
+                    next.push_back(it);
+                }
+                level.swap(next);
+                ++extra;
+            }
+            device_root = level[0].ref;
+            max_tlas_depth += extra;
+            if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the traversal stack");
+        }
     } else {
         // emit a built subtree as DNodes; returns the reference its parent stores. leaf_ref(first, count) names a leaf.
         struct Emit {
@@ -933,17 +971,18 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
                 prims[i].ref = bl.first_tri + i;
                 leaf_bounds(s, MRT_REF(MRT_PRIM_TRIANGLE, bl.first_tri + i), prims[i].lo, prims[i].hi);
             }
-            mrt_build::Builder b(prims, 4, 40, 1.0f);
+            mrt_build::Builder b(prims, (int)ctx->opt_leaf_tris, 40, (float)ctx->opt_tri_cost * 0.01f);
             int32_t root = b.build(0, prims.size(), 0);
             max_blas_depth = std::max(max_blas_depth, std::max(b.depth_of(root), 1));
             for (uint32_t i = 0; i < bl.n_tris; ++i) tri_map[bl.first_tri + i] = prims[i].ref;  // device order = leaf order, inside the BLAS's own range
             const uint32_t base = bl.first_tri;
             blas_root[bi] = emit_tree(b, root, [base](uint32_t first, uint32_t count) { return MRT_REF(MRT_PRIM_TRIANGLE, base + first) | ((count - 1u) << 27); });
         }
+        // TLAS: one SAH tree over every object of the world, one object per leaf -- whether the caller passed World::build_bvh's
+        // tree (world.rs:117-122) or the plain object list that World::intersect loops over (world.rs:135-140).
         max_tlas_depth = 0;
-        for (uint32_t ri = 0; ri < s->n_roots; ++ri) {  // TLAS: every root that is a BVH is rebuilt over its own leaves, one object per leaf
-            if (MRT_REF_KIND(roots[ri]) != MRT_PRIM_NODE) continue;
-            std::vector<mrt_build::Prim> prims;
+        std::vector<mrt_build::Prim> prims;
+        for (uint32_t ri = 0; ri < s->n_roots; ++ri) {
             std::vector<uint32_t> st{roots[ri]};
             while (!st.empty()) {
                 uint32_t ref = st.back();
@@ -959,14 +998,15 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
                     prims.push_back(p);
                 }
             }
+        }
+        if (!prims.empty()) {
             mrt_build::Builder b(prims, 1, 28, 4.0f);
             int32_t root = b.build(0, prims.size(), 0);
-            max_tlas_depth = std::max(max_tlas_depth, std::max(b.depth_of(root), 1));
+            max_tlas_depth = std::max(b.depth_of(root), 1);
             const std::vector<mrt_build::Prim>* pp = &prims;
-            roots[ri] = emit_tree(b, root, [pp](uint32_t first, uint32_t) { return (*pp)[first].ref; });
+            device_root = emit_tree(b, root, [pp](uint32_t first, uint32_t) { return (*pp)[first].ref; });
         }
-        if (max_tlas_depth + max_blas_depth + 2 + (int)std::min<uint32_t>(s->n_roots, 8) > kStackSize)
-            return fail(ctx, MRT_E_UNSUPPORTED, "rebuilt BVH too deep for the traversal stack");
+        if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return fail(ctx, MRT_E_UNSUPPORTED, "rebuilt BVH too deep for the traversal stack");
     }
     // which triangles can fail Material::alpha_test (geom.rs:567-571): UV'd, and their own material's surface can return alpha 0
     std::vector<int8_t> surf_alpha(s->n_surfaces, -1), mat_alpha(s->n_materials, -1);
@@ -1045,15 +1085,10 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if ((rc = upload(ctx, s->surfaces, (size_t)s->n_surfaces, &d.surfaces))) return rc;
     if ((rc = upload(ctx, s->textures, (size_t)s->n_textures, &d.textures))) return rc;
     if ((rc = upload(ctx, reinterpret_cast<const float4*>(s->texels), (size_t)s->n_texels, &d.texels))) return rc;
-    d.n_roots = s->n_roots;
+    d.root = device_root;
     d.n_volumes = (uint32_t)s->n_volumes;
     d.has_alpha = any_alpha;
-    d.roots_ext = nullptr;
-    if (s->n_roots <= 8) {
-        for (uint32_t i = 0; i < s->n_roots; ++i) d.roots[i] = roots[i];
-    } else if ((rc = upload(ctx, roots.data(), roots.size(), &d.roots_ext))) {
-        return rc;
-    }
+    d.slow = (any_alpha || s->n_volumes) ? 1u : 0u;
     d.bg = s->background;
     MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
     ctx->scene = d;
@@ -1099,8 +1134,8 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
-    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst, ctx->opt_finish_paths};
-    if (ctx->scene.has_alpha) k_aov<true><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths};
+    if (ctx->scene.slow) k_aov<true><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     else k_aov<false><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     AOV_TRY(cudaGetLastError());
     if (albedo) AOV_TRY(cudaMemcpyAsync(albedo, d_alb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1169,7 +1204,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     if ((rc = ensure_pool(ctx, total))) return rc;
     st.pool_slots = ctx->pool.slots;
     Pool pool = ctx->pool;
-    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_node_lanes, ctx->opt_node_burst, ctx->opt_finish_paths};
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths};
 
     QueueState init;
     std::memset(&init, 0, sizeof init);
@@ -1192,14 +1227,14 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
             k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, rp.finish_paths);
             if (rp.finish_paths) {
-                if (ctx->scene.has_alpha) k_finish<true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                if (ctx->scene.slow) k_finish<true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 else k_finish<false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 st.kernel_launches++;
             }
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[0], ctx->stream));
             k_generate<<<ctx->grid_generate, 256, 0, ctx->stream>>>(ctx->cam, rp, pool, ctx->d_q, cur);
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[1], ctx->stream)); MRT_CUDA(cudaEventRecord(e[2], ctx->stream)); }
-            const bool alpha = ctx->scene.has_alpha != 0;
+            const bool alpha = ctx->scene.slow != 0;
             if (ctx->opt_count && alpha) k_extend<true, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             else if (ctx->opt_count) k_extend<true, false><<<ctx->grid_extend_count, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             else if (alpha) k_extend<false, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
@@ -1321,13 +1356,13 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             if (value > (1u << 22)) return fail(ctx, MRT_E_INVALID, "finish threshold out of range [0, 2^22]");
             ctx->opt_finish_paths = (uint32_t)value;
             return MRT_OK;
-        case MRT_OPT_NODE_BURST:
-            if (value < 1 || value > 64) return fail(ctx, MRT_E_INVALID, "burst out of range [1, 64]");
-            ctx->opt_node_burst = (uint32_t)value;
+        case MRT_OPT_BVH_LEAF_TRIS:
+            if (value < 1 || value > 4) return fail(ctx, MRT_E_INVALID, "leaf size out of range [1, 4]");
+            ctx->opt_leaf_tris = (uint32_t)value;
             return MRT_OK;
-        case MRT_OPT_NODE_LANES:
-            if (value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [0, 32]");
-            ctx->opt_node_lanes = (uint32_t)value;
+        case MRT_OPT_BVH_TRI_COST:
+            if (value < 1 || value > 10000) return fail(ctx, MRT_E_INVALID, "triangle cost out of range [1, 10000]");
+            ctx->opt_tri_cost = (uint32_t)value;
             return MRT_OK;
         default: return fail(ctx, MRT_E_INVALID, "unknown option");
     }

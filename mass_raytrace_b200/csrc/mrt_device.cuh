@@ -59,11 +59,10 @@ struct DScene {
     const mrt_surface* surfaces;
     const mrt_texture* textures;
     const float4* texels;
-    uint32_t roots[8];
-    uint32_t n_roots;
+    uint32_t root;                       // the one root reference (node or single primitive); kNone = empty world
     uint32_t n_volumes;
-    uint32_t has_alpha;                  // some triangle carries kTriAlphaFlag: the ALPHA kernel variants are used
-    const uint32_t* roots_ext;  // when n_roots > 8
+    uint32_t has_alpha;                  // some triangle carries kTriAlphaFlag
+    uint32_t slow;                       // has_alpha || n_volumes: the SLOW kernel variants (RNG key carried through traversal) are used
     mrt_background bg;
 };
 struct DCamera {
@@ -196,24 +195,34 @@ __device__ __forceinline__ bool triangle_test(const DTriVerts& tv, const Ray& r,
     return true;
 }
 
-// BoundingBox::hit geom.rs:218-247 for two boxes at once. NaN handling follows f32::min/max (= fminf/fmaxf).
-// (b - o) * inv_d keeps the reference's inf/NaN pattern for d == 0 (0 * inf = NaN like 0 / 0; x * inf = x / 0).
-__device__ __forceinline__ void slab2(const DNode& n, V3 o, V3 id, float t_min, float t_max, bool& h0, bool& h1, float& n0, float& n1) {
-    const float kWiden = 4.76837158203125e-7f;  // 2^-21: four ulp of slack either side
-    float a0 = (n.xy0.x - o.x) * id.x, b0 = (n.xy0.y - o.x) * id.x;
-    float a1 = (n.xy1.x - o.x) * id.x, b1 = (n.xy1.y - o.x) * id.x;
+// BoundingBox::hit geom.rs:218-247 for two boxes at once, as a CONSERVATIVE test. NaN handling follows f32::min/max (= fminf/fmaxf).
+// The reference computes (b - o) / d per plane. Here each plane costs one FMA: b * id + ood with id ~ 1/d (MUFU.RCP, <= 1 ulp) and
+// ood = -(o * id), both per ray. Against the reference's value t the result is off by at most 2.5 * 2^-23 * (|t| + |o/d|)
+// (rounding of id, of ood and of the FMA, plus the reference's own two roundings), so the interval is widened by
+// 2^-21 * |t| relatively and by E2 = 2 * 2^-21 * max_axis |o * id| absolutely: the test never rejects a box the reference's
+// test accepts, and nothing computed here reaches a hit record. For d == 0: b * inf - o * inf is +-inf like the reference's
+// x / 0, or NaN (then the axis is ignored, which only accepts more); SlabRay keeps non-finite |o * id| out of E2.
+struct SlabRay {
+    V3 id;     // ~ 1 / direction
+    V3 ood;    // -(origin * id)
+    float e2;  // absolute slack
+};
+__device__ __forceinline__ void slab2(const DNode& n, const SlabRay& s, float t_min, float t_max, bool& h0, bool& h1, float& n0, float& n1) {
+    const float kWiden = 4.76837158203125e-7f;  // 2^-21
+    float a0 = fmaf(n.xy0.x, s.id.x, s.ood.x), b0 = fmaf(n.xy0.y, s.id.x, s.ood.x);
+    float a1 = fmaf(n.xy1.x, s.id.x, s.ood.x), b1 = fmaf(n.xy1.y, s.id.x, s.ood.x);
     float tn0 = fmaxf(fminf(a0, b0), t_min), tf0 = fminf(fmaxf(a0, b0), t_max);
     float tn1 = fmaxf(fminf(a1, b1), t_min), tf1 = fminf(fmaxf(a1, b1), t_max);
-    a0 = (n.xy0.z - o.y) * id.y; b0 = (n.xy0.w - o.y) * id.y;
-    a1 = (n.xy1.z - o.y) * id.y; b1 = (n.xy1.w - o.y) * id.y;
+    a0 = fmaf(n.xy0.z, s.id.y, s.ood.y); b0 = fmaf(n.xy0.w, s.id.y, s.ood.y);
+    a1 = fmaf(n.xy1.z, s.id.y, s.ood.y); b1 = fmaf(n.xy1.w, s.id.y, s.ood.y);
     tn0 = fmaxf(fminf(a0, b0), tn0); tf0 = fminf(fmaxf(a0, b0), tf0);
     tn1 = fmaxf(fminf(a1, b1), tn1); tf1 = fminf(fmaxf(a1, b1), tf1);
-    a0 = (n.z01.x - o.z) * id.z; b0 = (n.z01.y - o.z) * id.z;
-    a1 = (n.z01.z - o.z) * id.z; b1 = (n.z01.w - o.z) * id.z;
+    a0 = fmaf(n.z01.x, s.id.z, s.ood.z); b0 = fmaf(n.z01.y, s.id.z, s.ood.z);
+    a1 = fmaf(n.z01.z, s.id.z, s.ood.z); b1 = fmaf(n.z01.w, s.id.z, s.ood.z);
     tn0 = fmaxf(fminf(a0, b0), tn0); tf0 = fminf(fmaxf(a0, b0), tf0);
     tn1 = fmaxf(fminf(a1, b1), tn1); tf1 = fminf(fmaxf(a1, b1), tf1);
-    h0 = fmaf(-fabsf(tn0), kWiden, tn0) <= fmaf(fabsf(tf0), kWiden, tf0);
-    h1 = fmaf(-fabsf(tn1), kWiden, tn1) <= fmaf(fabsf(tf1), kWiden, tf1);
+    h0 = fmaf(-fabsf(tn0), kWiden, tn0) <= fmaf(fabsf(tf0), kWiden, tf0) + s.e2;
+    h1 = fmaf(-fabsf(tn1), kWiden, tn1) <= fmaf(fabsf(tf1), kWiden, tf1) + s.e2;
     n0 = tn0;
     n1 = tn1;
 }
@@ -255,7 +264,18 @@ __device__ __forceinline__ float rcp_fast(float x) {
     asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ V3 inv_dir(V3 d) { return V3{rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z)}; }
+__device__ __forceinline__ SlabRay slab_ray(const Ray& r) {
+    SlabRay s;
+    s.id = V3{rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z)};
+    const float px = r.o.x * s.id.x, py = r.o.y * s.id.y, pz = r.o.z * s.id.z;
+    s.ood = V3{-px, -py, -pz};
+    const float big = 3.0e38f;  // inf and NaN products (d == 0) carry no rounding error: they stay out of the slack
+    float m = (fabsf(px) < big) ? fabsf(px) : 0.0f;
+    m = fmaxf(m, (fabsf(py) < big) ? fabsf(py) : 0.0f);
+    m = fmaxf(m, (fabsf(pz) < big) ? fabsf(pz) : 0.0f);
+    s.e2 = m * 9.5367431640625e-7f;  // 2 * 2^-21 * max |o * id|
+    return s;
+}
 
 // Closest hit over World.objects (world.rs:131-144) through the flattened TLAS / BLAS, as a resumable state machine whose
 // three kinds of work are separate functions, so that a warp can run each kind with as many lanes as possible (k_extend):
@@ -264,60 +284,61 @@ __device__ __forceinline__ V3 inv_dir(V3 d) { return V3{rcp_fast(d.x), rcp_fast(
 //   trav_leaf  one primitive: triangle / sphere / volume test, or instance entry    -> T.ref = none | BLAS root
 // Differences from BvhNode::intersect (geom.rs:186-200), none of which can change a closest hit except on exact-t ties:
 // iterative with an explicit per-thread stack, nearer child first, subtree skipped when its box lies beyond the current closest t.
+// The world always has ONE root on the device (mrt_scene_upload puts a tree over a multi-object world list, world.rs:135-140).
 struct Traversal {
     Ray r;              // ray in the current space (world, or the entered instance's)
-    V3 id;              // reciprocal direction for the slab test
-    Ray w;              // the world-space ray and its reciprocal direction (restored when an instance is left)
-    V3 wid;
+    SlabRay s;          // its slab-test constants
     HitRec best;        // best.t doubles as the shrinking t_max (world.rs:133, geom.rs:192)
     uint32_t cur_inst;
     uint32_t ref;          // what this lane does next: a node ref, a leaf ref, or kNone = pop
-    uint32_t linear_next;  // next entry of a > 8-object pre-BVH world list (world.rs:135-140), else n_roots
     int sp;
     int inst_base;         // stack height when the current instance was entered (0 in world space)
 };
+// Where the world-space ray lives while the traversal is inside an instance (it is needed again when the instance is left):
+// in registers (k_aov, k_finish) or in shared memory (k_extend, which is register-bound).
+struct WorldRayRegs {
+    Ray w;
+    __device__ __forceinline__ Ray load() const { return w; }
+    __device__ __forceinline__ void store(const Ray& r) { w = r; }
+};
+template <int STRIDE>
+struct WorldRayShared {  // component-major: base[k * STRIDE] is component k of this thread's ray (conflict-free)
+    float* base;
+    __device__ __forceinline__ Ray load() const {
+        return Ray{V3{base[0], base[STRIDE], base[2 * STRIDE]}, V3{base[3 * STRIDE], base[4 * STRIDE], base[5 * STRIDE]}};
+    }
+    __device__ __forceinline__ void store(const Ray& r) {
+        base[0] = r.o.x; base[STRIDE] = r.o.y; base[2 * STRIDE] = r.o.z;
+        base[3 * STRIDE] = r.d.x; base[4 * STRIDE] = r.d.y; base[5 * STRIDE] = r.d.z;
+    }
+};
 __device__ __forceinline__ bool ref_is_node(uint32_t ref) { return ref < (1u << 29); }  // kind 0 in the top three bits
 
-__device__ __forceinline__ void trav_begin(const DScene& sc, Traversal& T, uint32_t* stack, const Ray& world, float t_max) {
+template <class W>
+__device__ __forceinline__ void trav_begin(const DScene& sc, Traversal& T, W& ws, const Ray& world, float t_max) {
+    ws.store(world);
     T.sp = 0;
-    T.linear_next = sc.n_roots;
-    if (sc.n_roots <= 8) {
-        for (int i = (int)sc.n_roots - 1; i >= 0; --i) stack[T.sp++] = sc.roots[i];
-    } else {
-        T.linear_next = 0;
-    }
     T.best = HitRec{t_max, kNone, kNone};
-    T.w = world;
-    T.wid = inv_dir(world.d);
-    T.r = T.w;
-    T.id = T.wid;
+    T.r = world;
+    T.s = slab_ray(world);
     T.cur_inst = kNone;
-    T.ref = kNone;
+    T.ref = sc.root;  // kNone for an empty world
     T.inst_base = 0;
 }
 
 // false when the traversal is complete (T.best is final). Entries pushed before an instance was entered sit below
 // T.inst_base: popping one of them means the BLAS is exhausted, i.e. Instance::intersect has returned (geom.rs:404-420).
-__device__ __forceinline__ bool trav_pop(const DScene& sc, Traversal& T, const uint32_t* stack) {
-    if (T.sp > 0) {
-        T.ref = stack[--T.sp];
-        if (T.sp < T.inst_base) {
-            T.r = T.w;
-            T.id = T.wid;
-            T.cur_inst = kNone;
-            T.inst_base = 0;
-        }
-        return true;
-    }
-    if (T.linear_next < sc.n_roots) {  // pre-BVH world list with more than 8 objects
-        T.ref = sc.roots_ext[T.linear_next++];
-        T.r = T.w;
-        T.id = T.wid;
+template <class W>
+__device__ __forceinline__ bool trav_pop(Traversal& T, const uint32_t* stack, const W& ws) {
+    if (T.sp == 0) return false;
+    T.ref = stack[--T.sp];
+    if (T.sp < T.inst_base) {
+        T.r = ws.load();
+        T.s = slab_ray(T.r);
         T.cur_inst = kNone;
         T.inst_base = 0;
-        return true;
     }
-    return false;
+    return true;
 }
 
 template <bool COUNT>
@@ -327,11 +348,11 @@ __device__ __forceinline__ void trav_node(const DScene& sc, Traversal& T, uint32
     n.xy0 = __ldg(&np->xy0);
     n.xy1 = __ldg(&np->xy1);
     n.z01 = __ldg(&np->z01);
-    uint4 ch = __ldg(reinterpret_cast<const uint4*>(&np->child0));
+    uint2 ch = __ldg(reinterpret_cast<const uint2*>(&np->child0));
     if (COUNT) cnt->node_visits++;
     bool h0, h1;
     float n0, n1;
-    slab2(n, T.r.o, T.id, t_min, T.best.t, h0, h1, n0, n1);
+    slab2(n, T.s, t_min, T.best.t, h0, h1, n0, n1);
     h0 = h0 && ch.x != kNone;
     h1 = h1 && ch.y != kNone;
     if (h0 && h1) {
@@ -346,8 +367,10 @@ __device__ __forceinline__ void trav_node(const DScene& sc, Traversal& T, uint32
 // Material::alpha_test of the triangle's OWN material at the candidate hit (geom.rs:567-571); defined after the surfaces below
 __device__ bool triangle_alpha_test(const DScene& sc, const DTriVerts& tv, uint32_t tri_dev, const Ray& r, float t, const RngKey& key);
 
-template <bool COUNT, bool ALPHA>
-__device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32_t* stack, float t_min, const RngKey& key, VisitCounters* cnt) {
+// SLOW = the scene has alpha-tested triangles or volumes: both draw random numbers during intersection (geom.rs:568, :638) and so
+// need the path's RNG key; scenes without them run the variant that carries no key and has neither code path.
+template <bool COUNT, bool SLOW, class W>
+__device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32_t* stack, const W& ws, float t_min, const RngKey& key, VisitCounters* cnt) {
     const uint32_t ref = T.ref;
     const uint32_t idx = MRT_REF_INDEX(ref);
     T.ref = kNone;
@@ -363,7 +386,7 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
                 tv.c = __ldg(&tp->c);
                 float t;
                 if (triangle_test(tv, T.r, t_min, T.best.t, t)) {
-                    if (ALPHA && (__float_as_uint(tv.a.w) & kTriAlphaFlag) && !triangle_alpha_test(sc, tv, first + k, T.r, t, key)) continue;  // geom.rs:567-571
+                    if (SLOW && (__float_as_uint(tv.a.w) & kTriAlphaFlag) && !triangle_alpha_test(sc, tv, first + k, T.r, t, key)) continue;  // geom.rs:567-571
                     T.best = HitRec{t, MRT_REF(MRT_PRIM_TRIANGLE, first + k), T.cur_inst};
                 }
             }
@@ -384,37 +407,40 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
             in.inv2 = __ldg(&ip->inv2);
             uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
             in.flags = meta.z;
-            T.r = to_instance_space(in, T.w);  // only reachable from world space (no nested instances, geom.rs:336)
-            T.id = inv_dir(T.r.d);
+            T.r = to_instance_space(in, T.r);  // only reachable from world space (no nested instances, geom.rs:336): T.r is the world ray
+            T.s = slab_ray(T.r);
             T.cur_inst = idx;
             T.inst_base = T.sp;
             T.ref = meta.x;  // BLAS root: a node
             break;
         }
         case MRT_PRIM_VOLUME: {
-            if (COUNT) cnt->volume_tests++;
-            mrt_volume vol = sc.volumes[idx];
-            Rand4 xi = draw4(key, kStreamVolume + idx);
-            float t;
-            if (volume_test(sc, vol, T.r, t_min, T.best.t, xi.x, t)) T.best = HitRec{t, ref, kNone};
+            if (SLOW) {
+                if (COUNT) cnt->volume_tests++;
+                mrt_volume vol = sc.volumes[idx];
+                Rand4 xi = draw4(key, kStreamVolume + idx);
+                float t;
+                if (volume_test(sc, vol, T.r, t_min, T.best.t, xi.x, t)) T.best = HitRec{t, ref, kNone};
+            }
             break;
         }
         default: break;
     }
 }
 
-// run a traversal to completion (AOV pass)
-template <bool COUNT, bool ALPHA>
+// run a traversal to completion (AOV pass, drain)
+template <bool COUNT, bool SLOW>
 __device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, float t_min, float t_max, const RngKey& key, VisitCounters* cnt) {
     uint32_t stack[kStackSize];
     Traversal T;
-    trav_begin(sc, T, stack, world, t_max);
-    while (trav_pop(sc, T, stack)) {
+    WorldRayRegs ws;
+    trav_begin(sc, T, ws, world, t_max);
+    do {
         while (T.ref != kNone) {
             if (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, t_min, cnt);
-            else trav_leaf<COUNT, ALPHA>(sc, T, stack, t_min, key, cnt);
+            else trav_leaf<COUNT, SLOW>(sc, T, stack, ws, t_min, key, cnt);
         }
-    }
+    } while (trav_pop(T, stack, ws));
     if (T.best.prim == kNone) T.best.t = t_max;
     return T.best;
 }

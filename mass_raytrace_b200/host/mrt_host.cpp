@@ -503,6 +503,47 @@ bool ply_read(const char* path, const int perm[3], std::vector<float>& out, floa
 
 }  // namespace
 
+namespace {
+
+// Texture::load_bytes texture.rs:70-97: RGBA8 -> RGBA f32 texels, byte / 255, no sRGB decode
+int surface_texture_rgba8(mrth_scene* s, const uint8_t* rgba, uint32_t w, uint32_t h, int wrap) {
+    if (!rgba || w == 0 || h == 0) { s->err = "empty texture"; return MRT_E_INVALID; }
+    if (wrap != MRT_WRAP_REPEAT && wrap != MRT_WRAP_CLAMP) { s->err = "Mirror wrapping is not implemented"; return MRT_E_UNSUPPORTED; }  // texture.rs:280
+    mrt_texture t{w, h, wrap, 0, s->texels.size() / 4};
+    size_t n = (size_t)w * h * 4;
+    s->texels.reserve(s->texels.size() + n);
+    for (size_t i = 0; i < n; ++i) s->texels.push_back((float)rgba[i] / 255.0f);  // texture.rs:79
+    s->textures.push_back(t);
+    return push_surface(s, MRT_SURF_TEXTURE, (int)s->textures.size() - 1, -1, 0, 0, 0, 0, 0);
+}
+
+// Model::new over Triangle::with_norms_and_uvs (geom.rs:468-496), one material per triangle
+int mesh_from_uv_faces(mrth_scene* s, const float* v, const float* nn, const float* uv, const int* materials, uint64_t n) {
+    if (n == 0 || n > 0x1FFFFFFFull - s->tri_shading.size()) { s->err = n ? "triangle count out of range" : "mesh has no triangles"; return MRT_E_INVALID; }
+    uint32_t first = (uint32_t)s->tri_shading.size();
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* p = v + 9 * i;
+        const float* t = uv + 6 * i;
+        s->tri_verts.insert(s->tri_verts.end(), p, p + 9);
+        mrt_tri_shading sh{};
+        std::memcpy(sh.normal, nn + 9 * i, 36);
+        std::memcpy(sh.uv, t, 24);
+        Vec3 ab = sub(load3(p + 3), load3(p)), ac = sub(load3(p + 6), load3(p));
+        float abu = t[2] - t[0], abv = t[3] - t[1], acu = t[4] - t[0], acv = t[5] - t[1];
+        float r = std::fmax(std::fmin(1.0f / (abu * acv - abv * acu), 1.0f), -1.0f);
+        store3(sh.tangent, scale(sub(scale(ab, acv), scale(ac, abv)), r));
+        store3(sh.bitangent, scale(sub(scale(ac, abu), scale(ab, acu)), r));
+        sh.material = materials[i];
+        sh.flags = MRT_TRI_HAS_UV;
+        s->tri_shading.push_back(sh);
+    }
+    return finish_mesh(s, first, (uint32_t)n);
+}
+
+#include "mrt_obj.inc"
+
+}  // namespace
+
 extern "C" {
 
 mrth_scene* mrth_scene_new(void) {
@@ -516,15 +557,12 @@ void mrth_seed(mrth_scene* s, uint64_t seed) { s->rng.state = seed; }
 float mrth_rand_f32(mrth_scene* s) { return s->rng.f32(); }
 
 int mrth_surface_solid(mrth_scene* s, float r, float g, float b, float a) { return push_surface(s, MRT_SURF_SOLID, -1, -1, 0, r, g, b, a); }
-int mrth_surface_texture(mrth_scene* s, const uint8_t* rgba, uint32_t w, uint32_t h, int wrap) {
-    if (!rgba || w == 0 || h == 0) { s->err = "empty texture"; return MRT_E_INVALID; }
-    if (wrap != MRT_WRAP_REPEAT && wrap != MRT_WRAP_CLAMP) { s->err = "Mirror wrapping is not implemented"; return MRT_E_UNSUPPORTED; }  // texture.rs:280
-    mrt_texture t{w, h, wrap, 0, s->texels.size() / 4};
-    size_t n = (size_t)w * h * 4;
-    s->texels.reserve(s->texels.size() + n);
-    for (size_t i = 0; i < n; ++i) s->texels.push_back((float)rgba[i] / 255.0f);  // texture.rs:79 (no sRGB decode)
-    s->textures.push_back(t);
-    return push_surface(s, MRT_SURF_TEXTURE, (int)s->textures.size() - 1, -1, 0, 0, 0, 0, 0);
+int mrth_surface_texture(mrth_scene* s, const uint8_t* rgba, uint32_t w, uint32_t h, int wrap) { return surface_texture_rgba8(s, rgba, w, h, wrap); }
+int mrth_surface_texture_png(mrth_scene* s, const char* path, int wrap) {  // Texture::load_png texture.rs:29-68
+    std::vector<uint8_t> rgba;
+    uint32_t w = 0, h = 0;
+    if (!png_decode_rgba8(path, rgba, w, h, s->err)) return MRT_E_INVALID;
+    return surface_texture_rgba8(s, rgba.data(), w, h, wrap);
 }
 int mrth_surface_ycbcr(mrth_scene* s, int luma, int chroma) {
     if (!valid_surface(s, luma) || !valid_surface(s, chroma)) return MRT_E_INVALID;
@@ -587,25 +625,53 @@ int mrth_mesh_new(mrth_scene* s, const float* v, uint64_t n, int tri_material) {
 }
 int mrth_mesh_new_uv(mrth_scene* s, const float* v, const float* nn, const float* uv, uint64_t n, int tri_material) {
     if (!valid_material(s, tri_material, false)) return MRT_E_INVALID;
-    if (n == 0 || n > 0x1FFFFFFFull - s->tri_shading.size()) { s->err = "triangle count out of range"; return MRT_E_INVALID; }
-    uint32_t first = (uint32_t)s->tri_shading.size();
-    for (uint64_t i = 0; i < n; ++i) {  // Triangle::with_norms_and_uvs geom.rs:468-496
-        const float* p = v + 9 * i;
-        const float* t = uv + 6 * i;
-        s->tri_verts.insert(s->tri_verts.end(), p, p + 9);
-        mrt_tri_shading sh{};
-        std::memcpy(sh.normal, nn + 9 * i, 36);
-        std::memcpy(sh.uv, t, 24);
-        Vec3 ab = sub(load3(p + 3), load3(p)), ac = sub(load3(p + 6), load3(p));
-        float abu = t[2] - t[0], abv = t[3] - t[1], acu = t[4] - t[0], acv = t[5] - t[1];
-        float r = std::fmax(std::fmin(1.0f / (abu * acv - abv * acu), 1.0f), -1.0f);
-        store3(sh.tangent, scale(sub(scale(ab, acv), scale(ac, abv)), r));
-        store3(sh.bitangent, scale(sub(scale(ac, abu), scale(ab, acu)), r));
-        sh.material = tri_material;
-        sh.flags = MRT_TRI_HAS_UV;
-        s->tri_shading.push_back(sh);
+    std::vector<int> mats((size_t)n, tri_material);
+    return mesh_from_uv_faces(s, v, nn, uv, mats.data(), n);
+}
+int mrth_mesh_load_obj(mrth_scene* s, const char* path, int wrap, const char* filtered_groups) {
+    ObjOptions opt{true, wrap, -1, {}};
+    if (filtered_groups) {  // newline-separated group names (SimpleTexturedBuilder::with_filter obj_loader.rs:174-186)
+        std::string all(filtered_groups), cur;
+        for (char c : all) {
+            if (c == '\n') { if (!cur.empty()) opt.filtered_groups.push_back(cur); cur.clear(); }
+            else cur.push_back(c);
+        }
+        if (!cur.empty()) opt.filtered_groups.push_back(cur);
     }
-    return finish_mesh(s, first, (uint32_t)n);
+    return load_obj(s, path, opt);
+}
+int mrth_mesh_load_obj_with(mrth_scene* s, const char* path, int tri_material) {
+    if (!valid_material(s, tri_material, false)) return MRT_E_INVALID;
+    return load_obj(s, path, ObjOptions{false, MRT_WRAP_REPEAT, tri_material, {}});
+}
+void mrth_mesh_get_shading(mrth_scene* s, int mesh, float* normals9, float* uvs6, int32_t* materials) {
+    const mrt_blas& b = s->blas.at((size_t)mesh);
+    for (uint32_t i = 0; i < b.n_tris; ++i) {
+        const mrt_tri_shading& sh = s->tri_shading[(size_t)b.first_tri + i];
+        if (normals9) std::memcpy(normals9 + 9 * (size_t)i, sh.normal, 36);
+        if (uvs6) std::memcpy(uvs6 + 6 * (size_t)i, sh.uv, 24);
+        if (materials) materials[i] = sh.material;
+    }
+}
+int mrth_material_info(mrth_scene* s, int material, float color4[4], uint32_t wh[2], uint64_t* texel_hash) {
+    if (!valid_material(s, material, false)) return MRT_E_INVALID;
+    const mrt_material& m = s->materials[(size_t)material];
+    color4[0] = color4[1] = color4[2] = color4[3] = 0.0f;
+    wh[0] = wh[1] = 0;
+    *texel_hash = 0;
+    if (m.surface >= 0) {
+        const mrt_surface& u = s->surfaces[(size_t)m.surface];
+        if (u.kind == MRT_SURF_SOLID) std::memcpy(color4, u.color, 16);
+        if (u.kind == MRT_SURF_TEXTURE) {
+            const mrt_texture& t = s->textures[(size_t)u.a];
+            wh[0] = t.width; wh[1] = t.height;
+            uint64_t h = 1469598103934665603ull;  // FNV-1a over the f32 texels
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(&s->texels[4 * (size_t)t.texel_offset]);
+            for (size_t i = 0; i < (size_t)t.width * t.height * 16; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+            *texel_hash = h;
+        }
+    }
+    return m.kind;
 }
 int mrth_mesh_load_ply(mrth_scene* s, const char* path, const int perm[3], int tri_material, float* max_abs) {
     if (!valid_material(s, tri_material, false)) return MRT_E_INVALID;

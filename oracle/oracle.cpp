@@ -1126,6 +1126,148 @@ static bool stl_load_binary(const std::string& path, const int perm[3], std::vec
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// obj_loader.rs — ObjLoader::load (:329-452) over the ObjBuilder trait (:23-43), with the two builders the reference ships:
+// SimpleTexturedBuilder (:160-308) and obj_fns / FnObjBuilder (:45-158). PNG decoding (`image` crate, texture.rs:36-39) is
+// not restated: decoded RGBA8 images are registered by path beforehand (orc_register_png) and load_png looks them up.
+// ---------------------------------------------------------------------------------------------
+struct ObjContext {  // :310-327
+    bool has_group = false, has_material = false, has_library = false;
+    std::string group_name, material_name, material_library;
+};
+struct ObjCorner { V3 vertex, normal; V2 uv; };
+struct ObjBuilder {
+    virtual ~ObjBuilder() {}
+    virtual bool include_group(const ObjContext&) { return true; }
+    virtual void load_materials(const ObjContext&) {}
+    virtual V2 build_uv(F x, F y) = 0;
+    virtual bool build_face(const ObjContext&, const ObjCorner& a, const ObjCorner& b, const ObjCorner& c, std::vector<Triangle>& out, std::string& err) = 0;
+};
+static std::vector<std::string> split_whitespace(const std::string& s) {
+    std::vector<std::string> out;
+    std::string cur;
+    for (char ch : s) {
+        if (std::isspace((unsigned char)ch)) { if (!cur.empty()) { out.push_back(cur); cur.clear(); } }
+        else cur.push_back(ch);
+    }
+    if (!cur.empty()) out.push_back(cur);
+    return out;
+}
+static bool rust_parse_f32(const std::string& t, F& out) {  // str::parse::<f32>: decimal literal, inf / infinity / nan, no hex, no blanks
+    if (t.empty()) return false;
+    size_t i = (t[0] == '+' || t[0] == '-') ? 1 : 0;
+    std::string body;
+    for (size_t k = i; k < t.size(); ++k) body.push_back((char)std::tolower((unsigned char)t[k]));
+    if (body == "inf" || body == "infinity") { out = t[0] == '-' ? -INF : INF; return true; }
+    if (body == "nan") { out = std::numeric_limits<F>::quiet_NaN(); return true; }
+    bool digit = false, dot = false, exp = false, exp_digit = false;
+    for (size_t k = 0; k < body.size(); ++k) {
+        char ch = body[k];
+        if (std::isdigit((unsigned char)ch)) { (exp ? exp_digit : digit) = true; }
+        else if (ch == '.' && !dot && !exp) dot = true;
+        else if (ch == 'e' && digit && !exp) { exp = true; if (k + 1 < body.size() && (body[k + 1] == '+' || body[k + 1] == '-')) ++k; }
+        else return false;
+    }
+    if (!digit || (exp && !exp_digit)) return false;
+    out = std::strtof(t.c_str(), nullptr);
+    return true;
+}
+static bool rust_parse_usize(const std::string& t, size_t& out) {
+    size_t i = (!t.empty() && t[0] == '+') ? 1 : 0;
+    if (i >= t.size()) return false;
+    unsigned long long v = 0;
+    for (; i < t.size(); ++i) {
+        if (!std::isdigit((unsigned char)t[i])) return false;
+        unsigned long long d = (unsigned long long)(t[i] - '0');
+        if (v > (~0ull - d) / 10) return false;
+        v = v * 10 + d;
+    }
+    out = (size_t)v;
+    return true;
+}
+static std::string path_with_file_name(const std::string& path, const std::string& name) {
+    size_t slash = path.rfind('/');
+    return slash == std::string::npos ? name : path.substr(0, slash + 1) + name;
+}
+static bool obj_load(const std::string& path, ObjBuilder& builder, std::vector<Triangle>& faces, std::string& err) {  // :332-452
+    std::ifstream file(path, std::ios::binary);
+    if (!file) { err = "cannot open " + path; return false; }
+    std::vector<V3> vertexes, normals;
+    std::vector<V2> uvs;
+    ObjContext context;
+    bool include_faces = builder.include_group(context);
+    std::string line;
+    while (std::getline(file, line)) {
+        std::vector<std::string> parts = split_whitespace(line);
+        if (parts.empty()) continue;
+        const std::string& head = parts[0];
+        auto num = [&](size_t i, F& v) { return i < parts.size() && rust_parse_f32(parts[i], v); };
+        if (head == "v") {  // :355-366
+            F x, y, z;
+            if (!(num(1, x) && num(2, y) && num(3, z))) { err = "unable to parse vertex: " + trim(line); return false; }
+            vertexes.push_back({x, y, z});
+        } else if (head == "vn") {  // :367-378
+            F x, y, z;
+            if (!(num(1, x) && num(2, y) && num(3, z))) { err = "unable to parse normal: " + trim(line); return false; }
+            normals.push_back({x, y, z});
+        } else if (head == "vt") {  // :379-389
+            F u, v;
+            if (!(num(1, u) && num(2, v))) { err = "unable to parse texture coord: " + trim(line); return false; }
+            uvs.push_back(builder.build_uv(u, v));
+        } else if (head == "f") {  // :390-429
+            if (!include_faces) continue;
+            auto read_face = [&](size_t pi, ObjCorner& out) -> bool {
+                if (pi >= parts.size()) return false;
+                const std::string& s = parts[pi];
+                std::vector<size_t> splits;  // s.split('/').filter_map(|n| n.parse::<usize>().ok())
+                size_t start = 0;
+                for (;;) {
+                    size_t p = s.find('/', start);
+                    size_t v;
+                    if (rust_parse_usize(s.substr(start, p == std::string::npos ? std::string::npos : p - start), v)) splits.push_back(v);
+                    if (p == std::string::npos) break;
+                    start = p + 1;
+                }
+                auto get = [](auto& vec, size_t one_based) { return one_based >= 1 && one_based <= vec.size() ? &vec[one_based - 1] : nullptr; };
+                const V3* v = nullptr;
+                const V3* n = nullptr;
+                const V2* uv = nullptr;
+                if (s.find("//") != std::string::npos) {  // :399-407: vertex, uvs.get(0), normal
+                    if (splits.size() > 0) v = get(vertexes, splits[0]);
+                    uv = uvs.empty() ? nullptr : &uvs[0];
+                    if (splits.size() > 1) n = get(normals, splits[1]);
+                } else {  // :408-416
+                    if (splits.size() > 0) v = get(vertexes, splits[0]);
+                    if (splits.size() > 1) uv = get(uvs, splits[1]);
+                    if (splits.size() > 2) n = get(normals, splits[2]);
+                }
+                if (!v || !n || !uv) return false;
+                out = {*v, *n, *uv};
+                return true;
+            };
+            ObjCorner a, b, c;
+            if (!(read_face(1, a) && read_face(2, b) && read_face(3, c))) { err = "unable to parse face: " + trim(line); return false; }
+            if (!builder.build_face(context, a, b, c, faces, err)) return false;
+        } else if (head == "o" || head == "g") {  // :430-435
+            if (parts.size() > 1) {
+                context.group_name = parts[1];
+                context.has_group = true;
+                include_faces = builder.include_group(context);
+            }
+        } else if (head == "usemtl") {  // :436-440
+            if (parts.size() > 1) { context.material_name = parts[1]; context.has_material = true; }
+        } else if (head == "mtllib") {  // :441-445
+            std::string joined;
+            for (size_t i = 1; i < parts.size(); ++i) { if (i > 1) joined += " "; joined += parts[i]; }
+            context.material_library = path_with_file_name(path, joined);
+            context.has_library = true;
+            builder.load_materials(context);
+        }
+    }
+    return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1141,6 +1283,8 @@ struct orc_scene {
     World world;
     Camera camera;
     bool bvh_built = false;
+    struct Png { std::string path; std::vector<uint8_t> rgba; uint32_t w, h; };
+    std::vector<Png> pngs;  // images decoded by the caller, looked up by Texture::load_png's path (orc_register_png)
 };
 
 namespace {
@@ -1178,6 +1322,93 @@ void add_counters(orc_counters& a, const orc_counters& b) {
     a.sphere_tests += b.sphere_tests; a.instance_tests += b.instance_tests; a.volume_tests += b.volume_tests;
 }
 }  // namespace
+
+namespace {
+// Texture::load_png texture.rs:29-68 over a pre-decoded image
+const Surface* load_png(orc_scene* s, const std::string& path, int wrapping, std::string& err) {
+    for (const orc_scene::Png& p : s->pngs)
+        if (p.path == path) { push_surface(s, new Texture(p.rgba.data(), p.w, p.h, wrapping)); return s->surfaces.back().get(); }
+    err = "cannot open " + path;
+    return nullptr;
+}
+struct SimpleTexturedBuilder : ObjBuilder {  // obj_loader.rs:160-308
+    orc_scene* s;
+    int wrapping;
+    std::vector<std::pair<std::string, const Surface*>> textures;
+    std::vector<std::pair<std::string, V3>> diffuse;
+    std::vector<std::string> filtered_groups;
+    template <class T>
+    static const T* lookup(const std::vector<std::pair<std::string, T>>& m, const std::string& k) {
+        for (auto it = m.rbegin(); it != m.rend(); ++it)  // HashMap::insert replaces: the last entry wins
+            if (it->first == k) return &it->second;
+        return nullptr;
+    }
+    bool process_material_library(const std::string& path, std::string& err) {  // :188-233
+        std::ifstream file(path, std::ios::binary);
+        if (!file) { err = "cannot open " + path; return false; }
+        std::string line, current_material;
+        bool has_current = false;
+        while (std::getline(file, line)) {
+            std::vector<std::string> parts = split_whitespace(trim(line));
+            if (parts.empty()) continue;
+            if (parts[0] == "newmtl") {
+                if (parts.size() > 1) { current_material = parts[1]; has_current = true; }
+            } else if (parts[0] == "Kd") {
+                if (has_current) {
+                    F x, y, z;
+                    if (parts.size() > 3 && rust_parse_f32(parts[1], x) && rust_parse_f32(parts[2], y) && rust_parse_f32(parts[3], z))
+                        diffuse.push_back({current_material, V3{x, y, z}});
+                }
+            } else if (parts[0] == "map_Kd") {
+                if (parts.size() > 1 && has_current) {
+                    const Surface* t = load_png(s, path_with_file_name(path, parts[1]), wrapping, err);
+                    if (!t) return false;  // `?` :226
+                    textures.push_back({current_material, t});
+                }
+            }
+        }
+        return true;
+    }
+    void load_materials(const ObjContext& context) override {  // :261-268
+        std::string err;
+        if (context.has_library && !process_material_library(context.material_library, err))
+            std::fprintf(stderr, "unable to load material library: %s\n", err.c_str());
+    }
+    V2 build_uv(F x, F y) override { return {x, 1.0f - y}; }  // :281-283
+    bool build_face(const ObjContext& context, const ObjCorner& a, const ObjCorner& b, const ObjCorner& c, std::vector<Triangle>& out, std::string& err) override {  // :285-298
+        const Surface* surface = nullptr;
+        if (context.has_material) {
+            if (const Surface* const* t = lookup(textures, context.material_name)) surface = *t;
+            else if (const V3* d = lookup(diffuse, context.material_name)) {
+                push_surface(s, new SolidColor(expand(*d, 1.0f)));
+                surface = s->surfaces.back().get();
+            }
+        }
+        if (!surface) { err = "No material found for face"; return false; }
+        push_material(s, new Lambertian(surface));
+        out.emplace_back(s->materials.back().get(), a.vertex, a.normal, a.uv, b.vertex, b.normal, b.uv, c.vertex, c.normal, c.uv);
+        return true;
+    }
+    bool include_group(const ObjContext& context) override {  // :300-306
+        if (!context.has_group) return true;
+        return std::find(filtered_groups.begin(), filtered_groups.end(), context.group_name) == filtered_groups.end();
+    }
+};
+struct FnObjBuilder : ObjBuilder {  // obj_fns(V3::new, V3::new, V2::new, |a, b, c| Triangle::with_norms_and_uvs(material, a, b, c))  :45-158, eve.rs:330-340
+    const Material* material;
+    V2 build_uv(F x, F y) override { return {x, y}; }
+    bool build_face(const ObjContext&, const ObjCorner& a, const ObjCorner& b, const ObjCorner& c, std::vector<Triangle>& out, std::string&) override {
+        out.emplace_back(material, a.vertex, a.normal, a.uv, b.vertex, b.normal, b.uv, c.vertex, c.normal, c.uv);
+        return true;
+    }
+};
+int mesh_from_faces(orc_scene* s, std::vector<Triangle>& faces) {
+    Mesh* m = new Mesh();
+    m->tris = std::move(faces);
+    return finish_mesh(s, m);
+}
+}  // namespace
+
 
 extern "C" {
 
@@ -1235,6 +1466,66 @@ int orc_mesh_new_uv(orc_scene* s, const float* v, const float* nn, const float* 
         m->tris.emplace_back(tm, v3(v + 9 * i), v3(nn + 9 * i), V2{uv[6 * i], uv[6 * i + 1]}, v3(v + 9 * i + 3), v3(nn + 9 * i + 3),
                              V2{uv[6 * i + 2], uv[6 * i + 3]}, v3(v + 9 * i + 6), v3(nn + 9 * i + 6), V2{uv[6 * i + 4], uv[6 * i + 5]});
     return finish_mesh(s, m);
+}
+void orc_register_png(orc_scene* s, const char* path, const uint8_t* rgba, uint32_t w, uint32_t h) {
+    s->pngs.push_back({path, std::vector<uint8_t>(rgba, rgba + (size_t)w * h * 4), w, h});
+}
+int orc_surface_texture_png(orc_scene* s, const char* path, int wrap_) {
+    return load_png(s, path, wrap_, s->err) ? (int)s->surfaces.size() - 1 : -1;
+}
+int orc_mesh_load_obj(orc_scene* s, const char* path, int wrap_, const char* filtered_groups) {
+    SimpleTexturedBuilder b;
+    b.s = s;
+    b.wrapping = wrap_;
+    if (filtered_groups) {
+        std::string cur;
+        for (const char* p = filtered_groups;; ++p) {
+            if (*p == '\n' || *p == 0) { if (!cur.empty()) b.filtered_groups.push_back(cur); cur.clear(); if (!*p) break; }
+            else cur.push_back(*p);
+        }
+    }
+    std::vector<Triangle> faces;
+    if (!obj_load(path, b, faces, s->err)) return -1;
+    return mesh_from_faces(s, faces);
+}
+int orc_mesh_load_obj_with(orc_scene* s, const char* path, int tri_material) {
+    FnObjBuilder b;
+    b.material = mat(s, tri_material);
+    std::vector<Triangle> faces;
+    if (!obj_load(path, b, faces, s->err)) return -1;
+    return mesh_from_faces(s, faces);
+}
+void orc_mesh_get_shading(orc_scene* s, int mesh, float* normals9, float* uvs6, int32_t* materials) {
+    const Mesh& m = *s->meshes.at((size_t)mesh);
+    for (size_t i = 0; i < m.tris.size(); ++i) {
+        const Triangle& t = m.tris[i];
+        if (normals9) { put3(normals9 + 9 * i, t.na); put3(normals9 + 9 * i + 3, t.nb); put3(normals9 + 9 * i + 6, t.nc); }
+        if (uvs6) { uvs6[6 * i] = t.uv_a.x; uvs6[6 * i + 1] = t.uv_a.y; uvs6[6 * i + 2] = t.uv_b.x; uvs6[6 * i + 3] = t.uv_b.y; uvs6[6 * i + 4] = t.uv_c.x; uvs6[6 * i + 5] = t.uv_c.y; }
+        if (materials) {
+            materials[i] = -1;
+            for (size_t k = 0; k < s->materials.size(); ++k)
+                if (s->materials[k].get() == t.material) { materials[i] = (int32_t)k; break; }
+        }
+    }
+}
+int orc_material_info(orc_scene* s, int material, float color4[4], uint32_t wh[2], uint64_t* texel_hash) {
+    const Material* m = mat(s, material);
+    color4[0] = color4[1] = color4[2] = color4[3] = 0.0f;
+    wh[0] = wh[1] = 0;
+    *texel_hash = 0;
+    const Surface* surface = nullptr;
+    int kind = -1;  // numbering of include/mrt.h's MRT_MAT_* for the kinds an OBJ can produce
+    if (auto* l = dynamic_cast<const Lambertian*>(m)) { kind = 1; surface = l->surface; }
+    else if (dynamic_cast<const Absorb*>(m)) kind = 0;
+    if (auto* c = dynamic_cast<const SolidColor*>(surface)) { color4[0] = c->c.x; color4[1] = c->c.y; color4[2] = c->c.z; color4[3] = c->c.w; }
+    if (auto* t = dynamic_cast<const Texture*>(surface)) {
+        wh[0] = t->w; wh[1] = t->h;
+        uint64_t h = 1469598103934665603ull;  // FNV-1a over the f32 texels
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(t->pixels.data());
+        for (size_t i = 0; i < t->pixels.size() * 16; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+        *texel_hash = h;
+    }
+    return kind;
 }
 int orc_mesh_load_ply(orc_scene* s, const char* path, const int perm[3], int tri_material, float* max_abs) {
     std::vector<V3> tv;

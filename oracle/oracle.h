@@ -75,6 +75,15 @@ int orc_mesh_new_uv(orc_scene*, const float* verts, const float* normals, const 
 int orc_mesh_load_ply(orc_scene*, const char* path, const int perm[3], int tri_material, float* max_abs);
 /* StlLoader::load_binary(path, |x,y,z| V3(v[perm]), |a,b,c| Triangle::new(material,a,b,c)) stl_loader.rs:10 */
 int orc_mesh_load_stl(orc_scene*, const char* path, const int perm[3], int tri_material);
+/* Texture::load_png texture.rs:29 — the `image` crate's decoder is not restated: the caller decodes (e.g. PIL) and registers RGBA8 by path */
+void orc_register_png(orc_scene*, const char* path, const uint8_t* rgba, uint32_t w, uint32_t h);
+int orc_surface_texture_png(orc_scene*, const char* path, int wrap);
+/* ObjLoader::load(path, SimpleTexturedBuilder::with_filter(wrap, groups)) obj_loader.rs:160-308, :332; groups newline-separated or NULL */
+int orc_mesh_load_obj(orc_scene*, const char* path, int wrap, const char* filtered_groups);
+/* ObjLoader::load(path, obj_fns(V3::new, V3::new, V2::new, |a,b,c| Triangle::with_norms_and_uvs(material,a,b,c))) obj_loader.rs:45, eve.rs:330 */
+int orc_mesh_load_obj_with(orc_scene*, const char* path, int tri_material);
+void orc_mesh_get_shading(orc_scene*, int mesh, float* normals9, float* uvs6, int32_t* materials);
+int orc_material_info(orc_scene*, int material, float color4[4], uint32_t wh[2], uint64_t* texel_hash);
 uint64_t orc_mesh_tri_count(orc_scene*, int mesh);
 void orc_mesh_get_verts(orc_scene*, int mesh, float* out9);            /* 9 floats per triangle */
 uint64_t orc_mesh_node_count(orc_scene*, int mesh);                    /* BvhNode count of the BLAS */

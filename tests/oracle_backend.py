@@ -23,6 +23,7 @@ _EXTRA = {
     "orc_render_aov": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _ffi.f32p, _ffi.f32p, _ffi.u32p, _ffi.u32p, _ffi.f32p, C.POINTER(orc_counters)]),
     "orc_render": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _ffi.f32p, _ffi.u32p, C.POINTER(orc_counters)]),
     "orc_resolve_rgb8": (None, [_ffi.f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _ffi.u8p]),
+    "orc_register_png": (None, [C.c_void_p, C.c_char_p, _ffi.u8p, C.c_uint32, C.c_uint32]),
     "orc_kat_sphere": (C.c_int, [C.c_float] * 4 + [C.POINTER(f3), C.POINTER(f3), C.c_float, C.c_float, _ffi.f32p]),
     "orc_kat_aabb": (C.c_int, [C.POINTER(f3)] * 4 + [C.c_float, C.c_float]),
     "orc_kat_triangle": (C.c_int, [_ffi.f32p, C.POINTER(f3), C.POINTER(f3), C.c_float, C.c_float, _ffi.f32p]),
@@ -63,6 +64,22 @@ class OracleScene(NativeScene):
 
     def __init__(self, world, camera=None):
         super().__init__(world, camera, backend=(oracle_lib(), "orc"))
+
+    # the oracle does not restate the `image` crate's PNG decoder: images are decoded here (PIL) and registered by path
+    def _prepare_png(self, path):
+        from PIL import Image
+
+        try:
+            arr = np.ascontiguousarray(np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8))
+        except OSError:
+            return  # unreadable / missing: the oracle reports "cannot open" like File::open would
+        self.lib.orc_register_png(self._h, path.encode(), arr.ctypes.data_as(_ffi.u8p), arr.shape[1], arr.shape[0])
+
+    def _prepare_obj(self, path):
+        d = os.path.dirname(path)
+        for name in sorted(os.listdir(d or ".")):
+            if name.lower().endswith(".png"):
+                self._prepare_png(os.path.join(d, name) if d else name)
 
     def render_aov(self, w, h, seed=1, threads=0):
         out = dict(albedo=np.zeros((h, w, 3), np.float32), normal=np.zeros((h, w, 3), np.float32), object=np.zeros((h, w), np.uint32),
