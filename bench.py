@@ -24,9 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # SURVEY.md §8d algorithmic bytes: 32 B per AABB test (one 64-B node fetch = two child boxes), 36 B per triangle test,
-# 16 B per sphere test, 64 B per instance entry; extend's own queue traffic per ray: slot index 4 + origin/direction 32 read,
-# hit record 16 + shade-queue entry 4 written.
-B_NODE_VISIT, B_TRI, B_SPHERE, B_INSTANCE, B_QUEUE_EXTEND = 64, 36, 16, 64, 56
+# 16 B per sphere test, 64 B per instance entry; extend's own queue traffic per ray: the 48-byte ray record read, the 64-byte
+# shade-queue entry (ray record + hit) written.
+B_NODE_VISIT, B_TRI, B_SPHERE, B_INSTANCE, B_QUEUE_EXTEND = 64, 36, 16, 64, 112
 
 WORKLOADS = {
     # name: (BASELINE.json config index, width, height, spp, description)
@@ -367,7 +367,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "spp_per_gpu_per_step": spp, "max_depth": 50,
                        "partition": f"samples per pixel split over {world_size} rank(s), one NCCL int64 sum-reduce per step" if world_size > 1 else "single GPU",
-                       "l2": "flushed between steps (256 MiB write); path-state pool (>= 268 MB at 4M slots) also exceeds the 126 MB L2",
+                       "l2": "flushed between steps (256 MiB write); the ray / shade queues of one iteration (>= 460 MB at 4M paths in flight) also exceed the 126 MB L2",
                        "scene_build_s": build_s, "rays_per_path": rays / paths},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -216,7 +216,7 @@ typedef struct mrt_stats {
     float shade_ms;
     float generate_ms;
     uint64_t scene_bytes;     /* device bytes of the uploaded scene */
-    uint64_t pool_slots;      /* path-state slots */
+    uint64_t pool_slots;      /* paths in flight (entries per ray queue) */
 } mrt_stats;
 
 typedef struct mrt_context mrt_context;
@@ -260,9 +260,8 @@ int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8
 enum {
     MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */
     MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
-    MRT_OPT_POOL_SLOTS = 3,   /* path-state slots (0 = default 2^22) */
+    MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^24 (0 = default 2^22) */
     MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes once at least this many of a warp's 32 lanes are idle (default 32: whole batches) */
-    MRT_OPT_SHADE_INORDER = 7, /* measurement aid: shade in slot order instead of through the material-sorted queues (slower) */
     MRT_OPT_BVH_LEAF_TRIS = 9, /* SAH rebuild at the next mrt_scene_upload: most triangles per BLAS leaf, 1..4 (default 4) */
     MRT_OPT_BVH_TRI_COST = 10, /* SAH rebuild: cost of one triangle test in hundredths of a node visit (default 100) */
     MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 65536, 0 = off) */

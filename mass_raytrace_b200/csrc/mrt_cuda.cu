@@ -3,23 +3,29 @@
 // Replaces render() (reference src/main.rs:150-295). One context drives one GPU:
 //
 //   advance  (1 thread)      queue bookkeeping, hands out the next block of pixel samples
-//   generate (persistent)    Camera::ray for regenerated path slots               world.rs:53-63, main.rs:258-260
-//   extend   (persistent)    closest hit through TLAS/BLAS, classify by material   world.rs:68, geom.rs
-//   shade    (persistent)    emit + scatter per material-sorted queue, accumulate  world.rs:69-77, material.rs
+//   generate (grid-stride)   Camera::ray for the new paths of this iteration          world.rs:53-63, main.rs:258-260
+//   extend   (persistent)    closest hit through TLAS/BLAS, classify by material      world.rs:68, geom.rs
+//   shade    (persistent)    emit + scatter per material-sorted queue, accumulate     world.rs:69-77, material.rs
 //
-// Path state lives in a fixed pool of slots (SoA, 64 B per slot). A slot whose path ends is refilled with the next
-// pixel sample in the same iteration ("regeneration"), so every extend launch works on a full pool until the job
-// drains. Queues hold slot indices; appends use one atomic per warp (ballot / match + popc + shuffle).
+// The queues carry the path state itself, not indices into a pool: an extend-queue entry is a 48-byte ray record (origin,
+// direction, throughput + pixel / sample / bounce), a shade-queue entry the same plus the 16-byte hit. Every kernel therefore
+// streams its input with coalesced 128-bit loads and appends its output with one atomic per warp (ballot / match + popc +
+// shuffle); nothing is gathered through a permuted index. A path that ends frees its place, and the next iteration generates as
+// many new camera rays as fit ("regeneration"), so every extend launch works on a full queue until the job drains.
 // Radiance is accumulated as 64-bit fixed point (2^-32 units) with integer atomics: sums are exact and therefore
 // independent of sample order, of how a sample range is split over calls, and of the number of GPUs.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mrt.h"
@@ -36,10 +42,10 @@ struct QueueState {
     uint32_t n_cont;       // continuing paths (written by the previous shade into the current extend queue)
     uint32_t n_new;        // camera rays generated this iteration
     uint32_t n_next;       // appended by shade for the next iteration
-    uint32_t n_free;       // slots released by shade
     uint32_t ext_cursor;   // persistent-warp fetch cursor of extend
     uint32_t done;
     uint32_t finish_n;     // > 0: the drain has started; k_finish runs these last paths to completion in one launch
+    uint32_t pad0;
     uint32_t n_shade[Q_COUNT + 3];
     unsigned long long next_work, total_work, gen_base;
     unsigned long long rays, iterations;
@@ -49,24 +55,26 @@ struct QueueState {
 struct RenderParams {
     uint32_t w, h, npix, spp_begin, max_depth;
     uint2 seed;
-    uint32_t refill_lanes;                          // k_extend hands rays to idle lanes once this many lanes of a warp are idle
-    uint32_t finish_paths;                          // drain threshold of k_finish (0 = never)
+    uint32_t refill_lanes;   // k_extend commits and refills finished lanes once this many lanes of a warp are idle
+    uint32_t finish_paths;   // drain threshold of k_finish (0 = never)
+    uint32_t capacity;       // rays in flight (entries per queue)
+    uint8_t region[Q_COUNT + 3];  // shade-queue region of each queue kind (only the material kinds the scene uses get one)
 };
 
-// One path = one 64-byte slot = two 32-byte sectors: extend reads sector 0 and writes `hit`; shade reads both and rewrites
-// sector 0 and `thr`. Slots are reached through permuted index queues, so every 32-byte sector fetched is fully used.
-struct __align__(16) Slot {
+// One path in flight. Extend queue entry = RayRec (48 B); shade queue entry = HitEntry (64 B = two 32-byte sectors).
+struct __align__(16) RayRec {
     float4 o;    // ray origin.xyz, pixel (as bits)
     float4 d;    // ray direction.xyz, sample index (as bits)
-    uint4 hit;   // t (as bits), prim ref, instance, material
     float4 thr;  // throughput.rgb, bounce (as bits)
 };
+struct __align__(16) HitEntry {
+    RayRec ray;
+    uint4 hit;  // t (as bits), prim ref, instance, material
+};
 struct Pool {
-    Slot* slot;
-    uint32_t* q_ext[2];
-    uint32_t* q_shade;  // Q_COUNT queues of `slots` entries
-    uint32_t* free_list;
-    uint32_t slots;
+    RayRec* q_ext[2];   // ping-pong: shade of iteration k appends to the queue extend reads in iteration k + 1
+    HitEntry* q_shade;  // `regions` regions of `capacity` entries
+    uint32_t capacity, regions;
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
@@ -96,25 +104,20 @@ __device__ __forceinline__ void accumulate(long long* accum, uint32_t* nonfinite
     }
 }
 
-__global__ void k_iota(uint32_t* p, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
-}
-
-__global__ void k_advance(QueueState* q, uint32_t finish_paths) {
+__global__ void k_advance(QueueState* q, uint32_t capacity, uint32_t finish_paths) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     q->rays += q->n_ext;
     uint32_t n_cont = q->n_next;
     q->n_next = 0;
     for (int k = 0; k < Q_COUNT; ++k) q->n_shade[k] = 0;
     unsigned long long remaining = q->total_work - q->next_work;
-    uint32_t n_new = (uint32_t)min((unsigned long long)q->n_free, remaining);
+    uint32_t n_new = (uint32_t)min((unsigned long long)(capacity - n_cont), remaining);  // regeneration: refill the places of ended paths
     q->gen_base = q->next_work;
     q->next_work += n_new;
-    q->n_free = 0;
     q->finish_n = 0;
     if (remaining == 0 && n_cont > 0 && n_cont <= finish_paths) {
         // the job is draining: no samples left to regenerate and only a few paths alive. Instead of up to max_depth more
-        // wavefront iterations over a nearly empty pool, k_finish runs each remaining path to its end in this iteration.
+        // wavefront iterations over a nearly empty queue, k_finish runs each remaining path to its end in this iteration.
         q->finish_n = n_cont;
         n_cont = 0;
     }
@@ -145,17 +148,15 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
                                                   QueueState* q, int cur) {
     const uint32_t n_new = q->n_new, n_cont = q->n_cont;
     const unsigned long long base = q->gen_base;
+    RayRec* __restrict__ out = pool.q_ext[cur] + n_cont;  // new paths follow the continuing ones: whole warps of neighbouring pixels
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-        uint32_t slot = pool.free_list[i];
         unsigned long long wk = base + i;
         uint32_t pixel = (uint32_t)(wk % rp.npix);
         uint32_t sample = rp.spp_begin + (uint32_t)(wk / rp.npix);
         Ray r = camera_ray(cam, rp, pixel, sample, true);
-        Slot* sl = &pool.slot[slot];
-        sl->o = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
-        sl->d = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(sample));
-        sl->thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
-        pool.q_ext[cur][n_cont + i] = slot;
+        out[i].o = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
+        out[i].d = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(sample));
+        out[i].thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
     }
 }
 
@@ -173,13 +174,17 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
 constexpr uint32_t kRefillLanes = 32;  // default; MRT_OPT_REFILL_LANES overrides it
 constexpr int kExtendThreads = 128;
 
-template <bool COUNT, bool SLOW>
-__global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
-                                                                                 QueueState* q, int cur) {
-    __shared__ float s_world[6 * kExtendThreads];  // world-space rays, needed again when a lane leaves an instance (keeps 6 registers free)
-    WorldRayShared<kExtendThreads> ws{&s_world[threadIdx.x]};
+template <bool COUNT, bool ALPHA, bool VOLUME>
+__global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ? 7 : 8)) k_extend(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp,
+                                                                                                  Pool pool, QueueState* q, int cur) {
+    // the path record of the ray each thread has in flight, component-major (conflict-free): 0-5 world-space ray (needed again
+    // when a lane leaves an instance), 6 pixel, 7 sample, 8-10 throughput, 11 bounce. It is copied to the shade queue at commit,
+    // so nothing but the traversal state occupies registers.
+    __shared__ float s_path[12 * kExtendThreads];
+    float* const mine = &s_path[threadIdx.x];
+    WorldRayShared<kExtendThreads> ws{mine};
     const uint32_t n = q->n_ext;
-    const uint32_t* __restrict__ queue = pool.q_ext[cur];
+    const RayRec* __restrict__ queue = pool.q_ext[cur];
     const float inf = __int_as_float(0x7f800000);
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -192,23 +197,21 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_exten
     T.ref = kNone;
     T.best = HitRec{inf, kNone, kNone};
     RngKey key{0u, 0u, 0u, rp.seed};
-    uint32_t slot = 0;
     bool active = false, pending = false, drained = false;
     for (;;) {
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle == 0xffffffffu || (!drained && (uint32_t)__popc(idle) >= refill_lanes)) {
-            // ---- commit finished rays: world.rs:68 result -> hit record, shade queue by material kind -----------
+            // ---- commit finished rays: world.rs:68 result -> shade queue of the hit material's kind --------------------
             uint32_t kind = 0xFFu;
+            HitRec h = T.best;
+            int32_t m = -1;
             if (pending) {
-                HitRec h = T.best;
                 if (h.prim == kNone) h.t = inf;
-                int32_t m = -1;
                 kind = Q_MISS;
                 if (h.prim != kNone) {
                     m = hit_material(sc, h);
                     kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
                 }
-                pool.slot[slot].hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
             }
             const uint32_t peers = __match_any_sync(0xffffffffu, kind);
             if (pending) {
@@ -216,10 +219,14 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_exten
                 uint32_t qbase = 0;
                 if (lane == leader) qbase = atomicAdd(&q->n_shade[kind], __popc(peers));
                 qbase = __shfl_sync(peers, qbase, leader);
-                pool.q_shade[(size_t)kind * pool.slots + qbase + __popc(peers & lt_mask)] = slot;
+                HitEntry* dst = pool.q_shade + (size_t)rp.region[kind] * pool.capacity + qbase + __popc(peers & lt_mask);
+                dst->ray.o = make_float4(mine[0], mine[kExtendThreads], mine[2 * kExtendThreads], mine[6 * kExtendThreads]);
+                dst->ray.d = make_float4(mine[3 * kExtendThreads], mine[4 * kExtendThreads], mine[5 * kExtendThreads], mine[7 * kExtendThreads]);
+                dst->ray.thr = make_float4(mine[8 * kExtendThreads], mine[9 * kExtendThreads], mine[10 * kExtendThreads], mine[11 * kExtendThreads]);
+                dst->hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
                 pending = false;
             }
-            // ---- refill idle lanes --------------------------------------------------------------------------------
+            // ---- refill idle lanes: consecutive queue entries, read with coalesced 128-bit loads -----------------------
             if (!drained) {
                 const uint32_t want = __popc(idle);
                 const uint32_t leader = __ffs(idle) - 1;
@@ -228,15 +235,20 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_exten
                 base = __shfl_sync(0xffffffffu, base, leader);
                 const uint32_t i = base + __popc(idle & lt_mask);
                 if (!active && i < n) {
-                    slot = queue[i];
-                    const Slot* sl = &pool.slot[slot];
-                    float4 o = sl->o, d = sl->d;
-                    if (SLOW) {
+                    const RayRec* rec = &queue[i];
+                    const float4 o = rec->o, d = rec->d, thr = rec->thr;
+                    if (ALPHA || VOLUME) {
                         key.pixel = __float_as_uint(o.w);
                         key.sample = __float_as_uint(d.w);
-                        key.bounce = __float_as_uint(sl->thr.w);
+                        key.bounce = __float_as_uint(thr.w);
                     }
-                    trav_begin(sc, T, ws, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, inf);  // world.rs:68: [0.001, +inf)
+                    mine[6 * kExtendThreads] = o.w;
+                    mine[7 * kExtendThreads] = d.w;
+                    mine[8 * kExtendThreads] = thr.x;
+                    mine[9 * kExtendThreads] = thr.y;
+                    mine[10 * kExtendThreads] = thr.z;
+                    mine[11 * kExtendThreads] = thr.w;
+                    trav_begin(sc, T, ws, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, inf);  // world.rs:68: [0.001, +inf); stores the ray in s_path 0-5
                     active = true;
                 }
                 drained = base + want >= n;
@@ -249,7 +261,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_exten
         }
         if (active) {
             while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
-            if (T.ref != kNone) trav_leaf<COUNT, SLOW>(sc, T, stack, ws, 0.001f, key, &cnt);
+            if (T.ref != kNone) trav_leaf<COUNT, ALPHA, VOLUME>(sc, T, stack, ws, 0.001f, key, &cnt);
         }
     }
     if (COUNT) {
@@ -265,11 +277,10 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || SLOW ? 1 : 8) k_exten
 }
 
 // One queue entry of Camera::trace's hit/miss handling (world.rs:69-77) in iterative form:
-// radiance += throughput * emitted; throughput *= attenuation.
-__device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams& rp, const Pool& pool, long long* accum, uint32_t* nonfinite,
-                                            uint32_t kind, uint32_t slot, bool& cont) {
-    Slot* sl = &pool.slot[slot];
-    float4 o = sl->o, d = sl->d, th = sl->thr;
+// radiance += throughput * emitted; throughput *= attenuation. On return with cont == true, `e.ray` is the scattered ray.
+__device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams& rp, long long* accum, uint32_t* nonfinite, uint32_t kind, HitEntry& e,
+                                            bool& cont) {
+    const float4 o = e.ray.o, d = e.ray.d, th = e.ray.thr;
     const uint32_t pixel = __float_as_uint(o.w), sample = __float_as_uint(d.w);
     uint32_t bounce = __float_as_uint(th.w);
     Ray ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}};
@@ -278,7 +289,7 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
     if (kind == Q_MISS) {  // world.rs:77
         accumulate(accum, nonfinite, pixel, thr * background(sc, ray));
     } else {
-        uint4 hr = sl->hit;
+        const uint4 hr = e.hit;
         HitRec h{__uint_as_float(hr.x), hr.y, hr.z};
         RngKey key{pixel, sample, bounce, rp.seed};
         mrt_material mat = sc.materials[(int32_t)hr.w];
@@ -296,9 +307,9 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
             bounce += 1;
             if (bounce < rp.max_depth) {  // world.rs:66: the next call would be depth == 0 -> contributes 0
                 cont = true;
-                sl->o = make_float4(s.point.x, s.point.y, s.point.z, o.w);
-                sl->d = make_float4(sco.dir.x, sco.dir.y, sco.dir.z, d.w);
-                sl->thr = make_float4(thr.x, thr.y, thr.z, __uint_as_float(bounce));
+                e.ray.o = make_float4(s.point.x, s.point.y, s.point.z, o.w);
+                e.ray.d = make_float4(sco.dir.x, sco.dir.y, sco.dir.z, d.w);
+                e.ray.thr = make_float4(thr.x, thr.y, thr.z, __uint_as_float(bounce));
             }
         }
     }
@@ -312,118 +323,81 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
 #ifndef MRT_SHADE_MINB
 #define MRT_SHADE_MINB 3
 #endif
-#ifndef MRT_SHADE_UNROLL
-#define MRT_SHADE_UNROLL 2
-#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Each warp takes 32 x MRT_SHADE_UNROLL consecutive entries of one material queue: the slot indices are read first and the slot
-// records prefetched, so the gathers of the later entries overlap the shading of the earlier ones; the surviving / finished slots
-// of the whole chunk are appended to the next extend queue / the free list with ONE atomic each.
+// Each warp takes 32 consecutive entries of one material queue at a time (so a warp shades one material kind), streams them in
+// with coalesced 128-bit loads -- the entries of its next turn are prefetched into L2 meanwhile -- and appends the scattered
+// rays of the surviving paths to the next extend queue with one atomic per warp.
 __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
                                                                             QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
-    constexpr int U = MRT_SHADE_UNROLL;
-    uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
+    RayRec* __restrict__ q_next = pool.q_ext[cur ^ 1];
     const uint32_t lane = lane_id(), lt_mask = (1u << lane) - 1u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    // the nine queue lengths: one load per lane, broadcast per kind (instead of nine dependent round trips per warp)
+    const uint32_t my_count = lane < Q_COUNT ? q->n_shade[lane] : 0u;
     for (uint32_t kind = 0; kind < Q_COUNT; ++kind) {
-        const uint32_t n = q->n_shade[kind];
-        const uint32_t* __restrict__ queue = pool.q_shade + (size_t)kind * pool.slots;
-        for (uint32_t base = warp * (32u * U); base < n; base += n_warps * (32u * U)) {
-            uint32_t slot[U];
-            bool valid[U], cont[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t i = base + (uint32_t)u * 32u + lane;
-                valid[u] = i < n;
-                slot[u] = valid[u] ? queue[i] : 0u;
-                if (valid[u]) prefetch_l2(&pool.slot[slot[u]]);
+        const uint32_t n = __shfl_sync(0xffffffffu, my_count, kind);
+        if (n == 0) continue;
+        const HitEntry* __restrict__ queue = pool.q_shade + (size_t)rp.region[kind] * pool.capacity;
+        for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {
+            const uint32_t i = base + lane;
+            const bool valid = i < n;
+            const uint32_t ahead = i + n_warps * 32u;
+            if (ahead < n) {
+                prefetch_l2(&queue[ahead]);
+                prefetch_l2(reinterpret_cast<const char*>(&queue[ahead]) + 32);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                cont[u] = false;
-                if (valid[u]) shade_entry(sc, rp, pool, accum, nonfinite, kind, slot[u], cont[u]);
-            }
-            uint32_t off_c[U], off_f[U], tot_c = 0, tot_f = 0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t mc = __ballot_sync(0xffffffffu, valid[u] && cont[u]), mf = __ballot_sync(0xffffffffu, valid[u] && !cont[u]);
-                off_c[u] = tot_c + __popc(mc & lt_mask);
-                off_f[u] = tot_f + __popc(mf & lt_mask);
-                tot_c += __popc(mc);
-                tot_f += __popc(mf);
-            }
-            uint32_t base_c = 0, base_f = 0;
-            if (lane == 0) {
-                if (tot_c) base_c = atomicAdd(&q->n_next, tot_c);
-                if (tot_f) base_f = atomicAdd(&q->n_free, tot_f);
-            }
-            base_c = __shfl_sync(0xffffffffu, base_c, 0);
-            base_f = __shfl_sync(0xffffffffu, base_f, 0);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (valid[u] && cont[u]) q_next[base_c + off_c[u]] = slot[u];
-                if (valid[u] && !cont[u]) pool.free_list[base_f + off_f[u]] = slot[u];
-            }
-        }
-    }
-}
-
-// MRT_OPT_SHADE_INORDER (measurement aid, off by default): shade in slot order -- coalesced 64-byte records but mixed material
-// kinds per warp -- instead of through the material-sorted index queues. Bit-identical images; 2x SLOWER on B200 (Cornell 21.9 vs
-// 11.1 ms, book-1 7.6 vs 3.1 ms per render), which is the measured case for material-sorted shading (profiles/README.md).
-constexpr uint32_t kProcessed = 0xFFFFFFFDu;
-__global__ void k_mark_processed(Pool pool) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pool.slots; i += gridDim.x * blockDim.x) pool.slot[i].hit.y = kProcessed;
-}
-__global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade_inorder(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp,
-                                                                                     Pool pool, QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
-    uint32_t* __restrict__ q_next = pool.q_ext[cur ^ 1];
-    const uint32_t n_round = (pool.slots + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        bool valid = i < pool.slots, cont = false;
-        if (valid) {
-            uint4 hr = pool.slot[i].hit;
-            valid = hr.y != kProcessed;
+            bool cont = false;
+            HitEntry e;
             if (valid) {
-                uint32_t kind = (hr.y == kNone) ? (uint32_t)Q_MISS : Q_FIRST_MAT + (uint32_t)sc.materials[(int32_t)hr.w].kind;
-                shade_entry(sc, rp, pool, accum, nonfinite, kind, i, cont);
-                pool.slot[i].hit.y = kProcessed;
+                e.ray.o = queue[i].ray.o;
+                e.ray.d = queue[i].ray.d;
+                e.ray.thr = queue[i].ray.thr;
+                e.hit = queue[i].hit;
+                shade_entry(sc, rp, accum, nonfinite, kind, e, cont);
+            }
+            const uint32_t mc = __ballot_sync(0xffffffffu, cont);
+            if (mc) {
+                uint32_t base_c = 0;
+                if (lane == 0) base_c = atomicAdd(&q->n_next, __popc(mc));
+                base_c = __shfl_sync(0xffffffffu, base_c, 0);
+                if (cont) {
+                    RayRec* dst = &q_next[base_c + __popc(mc & lt_mask)];
+                    dst->o = e.ray.o;
+                    dst->d = e.ray.d;
+                    dst->thr = e.ray.thr;
+                }
             }
         }
-        uint32_t at = warp_append(&q->n_next, valid && cont);
-        if (valid && cont) q_next[at] = i;
-        at = warp_append(&q->n_free, valid && !cont);
-        if (valid && !cont) pool.free_list[at] = i;
     }
 }
 
 // Drain: one thread per remaining path, each looping extend + shade until its path ends (paths are independent, so no
 // grid-wide step is needed). Launched every iteration; returns at once unless k_advance has set finish_n.
-template <bool SLOW>
+template <bool ALPHA, bool VOLUME>
 __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool, QueueState* q,
                                                 int cur, long long* accum, uint32_t* nonfinite) {
     const uint32_t n = q->finish_n;
     if (n == 0) return;
-    const uint32_t* __restrict__ queue = pool.q_ext[cur];
+    const RayRec* __restrict__ queue = pool.q_ext[cur];
     const float inf = __int_as_float(0x7f800000);
     unsigned long long rays = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = queue[i];
-        Slot* sl = &pool.slot[slot];
+        HitEntry e;
+        e.ray = queue[i];
         bool cont = true;
         while (cont) {
-            float4 o = sl->o, d = sl->d;
-            RngKey key{__float_as_uint(o.w), __float_as_uint(d.w), __float_as_uint(sl->thr.w), rp.seed};
-            HitRec h = traverse<false, SLOW>(sc, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, 0.001f, inf, key, nullptr);
+            const float4 o = e.ray.o, d = e.ray.d;
+            RngKey key{__float_as_uint(o.w), __float_as_uint(d.w), __float_as_uint(e.ray.thr.w), rp.seed};
+            HitRec h = traverse<false, ALPHA, VOLUME>(sc, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, 0.001f, inf, key, nullptr);
             int32_t m = -1;
             uint32_t kind = Q_MISS;
             if (h.prim != kNone) {
                 m = hit_material(sc, h);
                 kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
             }
-            sl->hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
-            shade_entry(sc, rp, pool, accum, nonfinite, kind, slot, cont);
+            e.hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
+            shade_entry(sc, rp, accum, nonfinite, kind, e, cont);
             ++rays;
         }
     }
@@ -432,7 +406,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene s
 }
 
 // PASS A (main.rs:166-222): Camera::albedo_normal (world.rs:81-93) at pixel centres
-template <bool SLOW>
+template <bool ALPHA, bool VOLUME>
 __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp,
                                              float* albedo, float* normal, uint32_t* object_id, uint32_t* tri_id, float* t_out) {
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,7 +414,7 @@ __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, 
     const float inf = __int_as_float(0x7f800000);
     Ray ray = camera_ray(cam, rp, pixel, 0u, false);
     RngKey key{pixel, 0u, 0u, rp.seed};
-    HitRec h = traverse<false, SLOW>(sc, ray, 0.001f, inf, key, nullptr);
+    HitRec h = traverse<false, ALPHA, VOLUME>(sc, ray, 0.001f, inf, key, nullptr);
     V3 a, n{0.0f, 0.0f, 0.0f};
     uint32_t obj = kNone, tri = kNone;
     float t = inf;
@@ -547,9 +521,18 @@ struct mrt_context {
     std::string err;
     int n_sms = 0;
     // scene
-    std::vector<void*> scene_allocs;
+    // scene arrays live in a grow-only device arena (one buffer per array kind) so that re-uploading a scene of similar size
+    // -- every frame of an animation, main.rs:104-117 -- costs no cudaMalloc / cudaFree; host data goes through two pinned
+    // staging chunks so that the copies are real DMA and overlap the host-side memcpy into the next chunk
+    struct DevBuf { void* p = nullptr; size_t cap = 0; };
+    std::vector<DevBuf> scene_bufs;
+    size_t scene_buf_next = 0;
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    int stage_next = 0;
     DScene scene{};
     bool has_scene = false;
+    uint32_t material_kinds = 0;  // bit per MRT_MAT_* kind present in the scene's material table
     DCamera cam{};
     bool has_camera = false;
     uint64_t scene_bytes = 0;
@@ -568,12 +551,12 @@ struct mrt_context {
     // options
     bool opt_count = false, opt_time = false;
     uint64_t opt_pool_slots = 0;
-    bool opt_shade_inorder = false;
     uint32_t opt_finish_paths = 65536;
     uint32_t opt_leaf_tris = 4, opt_tri_cost = 100;
     uint32_t opt_refill_lanes = kRefillLanes;
     mrt_stats stats{};
-    int grid_extend = 0, grid_extend_count = 0, grid_extend_slow = 0, grid_shade = 0, grid_generate = 0;
+    int grid_extend[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [count visits][0 plain, 1 volumes, 2 alpha-tested triangles (+ volumes)]
+    int grid_shade = 0, grid_generate = 0;
 };
 
 static std::string g_create_error;
@@ -592,29 +575,86 @@ static int fail(mrt_context* ctx, int code, const std::string& msg) {
     return code;
 }
 
+constexpr size_t kStageChunk = 32u << 20;
+
+// memcpy split over a few threads (one thread tops out near 10 GB/s; the scene arrays of a 10 M-triangle scene are ~2 GB)
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kMin = 4u << 20;
+    int parts = (int)std::min<size_t>(4, bytes / kMin);
+    if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    for (int k = 1; k < parts; ++k) {
+        size_t a = bytes * (size_t)k / (size_t)parts, b = bytes * (size_t)(k + 1) / (size_t)parts;
+        th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + a, static_cast<const char*>(src) + a, b - a); });
+    }
+    std::memcpy(dst, src, bytes / (size_t)parts);
+    for (auto& t : th) t.join();
+}
+
+// run fn(first, last) over [0, n) in parallel slices (host-side packing loops over millions of triangles)
+template <class Fn>
+static void parallel_for(size_t n, Fn fn) {
+    const size_t kMin = 1u << 16;
+    int parts = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), n / kMin);
+    if (parts <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int k = 1; k < parts; ++k) th.emplace_back([=] { fn(n * (size_t)k / (size_t)parts, n * (size_t)(k + 1) / (size_t)parts); });
+    fn((size_t)0, n / (size_t)parts);
+    for (auto& t : th) t.join();
+}
+
 template <class T>
 static int upload(mrt_context* ctx, const T* src, size_t n, const T** dst) {
     *dst = nullptr;
-    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-    void* p = nullptr;
-    MRT_CUDA(cudaMalloc(&p, bytes));
-    ctx->scene_allocs.push_back(p);
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (ctx->scene_buf_next >= ctx->scene_bufs.size()) ctx->scene_bufs.emplace_back();
+    mrt_context::DevBuf& buf = ctx->scene_bufs[ctx->scene_buf_next++];
+    if (buf.cap < bytes) {
+        if (buf.p) cudaFree(buf.p);
+        buf = mrt_context::DevBuf{};
+        const size_t cap = bytes + bytes / 8;  // a little headroom: an animated scene rarely keeps its exact size
+        MRT_CUDA(cudaMalloc(&buf.p, cap));
+        buf.cap = cap;
+    }
     ctx->scene_bytes += bytes;
-    if (n) MRT_CUDA(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    *dst = static_cast<const T*>(p);
+    const char* from = reinterpret_cast<const char*>(src);
+    for (size_t off = 0; off < n * sizeof(T); off += kStageChunk) {
+        const size_t len = std::min(kStageChunk, n * sizeof(T) - off);
+        const int k = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        if (!ctx->stage[k]) {
+            MRT_CUDA(cudaMallocHost(&ctx->stage[k], kStageChunk));
+            MRT_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+        } else {
+            MRT_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));  // the DMA that last read this chunk has finished
+        }
+        parallel_memcpy(ctx->stage[k], from + off, len);
+        MRT_CUDA(cudaMemcpyAsync(static_cast<char*>(buf.p) + off, ctx->stage[k], len, cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(cudaEventRecord(ctx->stage_ev[k], ctx->stream));
+    }
+    *dst = static_cast<const T*>(buf.p);
     return MRT_OK;
 }
 
+// the arena is kept for the next upload; only the context's destruction releases it
 static void free_scene(mrt_context* ctx) {
-    for (void* p : ctx->scene_allocs) cudaFree(p);
-    ctx->scene_allocs.clear();
+    ctx->scene_buf_next = 0;
     ctx->scene_bytes = 0;
     ctx->has_scene = false;
 }
+static void release_scene_arena(mrt_context* ctx) {
+    for (auto& b : ctx->scene_bufs) cudaFree(b.p);
+    ctx->scene_bufs.clear();
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+        if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+        ctx->stage[k] = nullptr;
+        ctx->stage_ev[k] = nullptr;
+    }
+}
 static void free_pool(mrt_context* ctx) {
     Pool& p = ctx->pool;
-    cudaFree(p.slot);
-    cudaFree(p.q_ext[0]); cudaFree(p.q_ext[1]); cudaFree(p.q_shade); cudaFree(p.free_list);
+    cudaFree(p.q_ext[0]); cudaFree(p.q_ext[1]); cudaFree(p.q_shade);
     p = Pool{};
 }
 static void free_image(mrt_context* ctx) {
@@ -676,12 +716,16 @@ int mrt_context_create(int device, void* stream, mrt_context** out) {
     if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return bail("cudaEventCreate", e);
     // persistent grids: SM count x resident blocks per SM
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false>, 128, 0);
-    ctx->grid_extend = ctx->n_sms * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, false>, 128, 0);
-    ctx->grid_extend_count = ctx->n_sms * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true, true>, 128, 0);
-    ctx->grid_extend_slow = ctx->n_sms * std::max(occ, 1);
+    auto extend_grid = [&](auto kernel) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kExtendThreads, 0);
+        return ctx->n_sms * std::max(occ, 1);
+    };
+    ctx->grid_extend[0][0] = extend_grid(k_extend<false, false, false>);
+    ctx->grid_extend[0][1] = extend_grid(k_extend<false, false, true>);
+    ctx->grid_extend[0][2] = extend_grid(k_extend<false, true, true>);
+    ctx->grid_extend[1][0] = extend_grid(k_extend<true, false, false>);
+    ctx->grid_extend[1][1] = extend_grid(k_extend<true, false, true>);
+    ctx->grid_extend[1][2] = extend_grid(k_extend<true, true, true>);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, MRT_SHADE_THREADS, 0);
     ctx->grid_shade = ctx->n_sms * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_generate, 256, 0);
@@ -696,6 +740,7 @@ void mrt_context_destroy(mrt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
+    release_scene_arena(ctx);
     free_pool(ctx);
     free_image(ctx);
     cudaFree(ctx->d_q);
@@ -781,6 +826,15 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if (!s) return fail(ctx, MRT_E_INVALID, "scene is NULL");
     if (s->abi_version != MRT_ABI_VERSION) return fail(ctx, MRT_E_INVALID, "mrt_scene_desc.abi_version mismatch");
     MRT_CUDA(cudaSetDevice(ctx->device));
+    // phase timing of the upload on stderr when MRT_UPLOAD_TIMING is set (measurement aid)
+    const bool timing = std::getenv("MRT_UPLOAD_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mrt_scene_upload: %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     // ---- validate ------------------------------------------------------------------------------------------
     if (s->n_nodes >= (1ull << 29) || s->n_tris >= (1ull << 29) || s->n_spheres >= (1ull << 29) || s->n_instances >= (1ull << 29))
         return fail(ctx, MRT_E_INVALID, "array too large for 29-bit primitive references");
@@ -814,8 +868,14 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     }
     for (uint64_t i = 0; i < s->n_spheres; ++i)
         if (!mat_ok(s->spheres[i].material, false)) return fail(ctx, MRT_E_INVALID, "sphere material out of range");
-    for (uint64_t i = 0; i < s->n_tris; ++i)
-        if (!mat_ok(s->tri_shading[i].material, false)) return fail(ctx, MRT_E_INVALID, "triangle material out of range");
+    {
+        std::atomic<bool> bad{false};
+        parallel_for((size_t)s->n_tris, [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; ++i)
+                if (!mat_ok(s->tri_shading[i].material, false)) bad = true;
+        });
+        if (bad) return fail(ctx, MRT_E_INVALID, "triangle material out of range");
+    }
     for (uint64_t i = 0; i < s->n_volumes; ++i) {
         const mrt_volume& v = s->volumes[i];
         if (!ref_ok(s, v.target, false)) return fail(ctx, MRT_E_INVALID, "volume target out of range");
@@ -828,10 +888,12 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
             if (!surf_ok(s->background.surface[k])) return fail(ctx, MRT_E_INVALID, "background surface out of range");
     std::string why;
     int blas_depth = 0;
+    const bool keep = (s->flags & MRT_SCENE_KEEP_TOPOLOGY) != 0;
     for (uint64_t i = 0; i < s->n_blas; ++i) {
         const mrt_blas& b = s->blas[i];
         if (MRT_REF_KIND(b.root) != MRT_PRIM_NODE || MRT_REF_INDEX(b.root) >= s->n_nodes || (uint64_t)b.first_tri + b.n_tris > s->n_tris)
             return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
+        if (!keep) continue;  // the SAH rebuild reads the BLAS's triangle range only, never the caller's nodes
         int d = subtree_depth(s, b.root, false, why);
         if (d < 0) return fail(ctx, MRT_E_INVALID, why);
         blas_depth = std::max(blas_depth, d);
@@ -847,15 +909,15 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         if (d < 0) return fail(ctx, MRT_E_INVALID, why);
         tlas_depth = std::max(tlas_depth, d);
     }
-    if (tlas_depth + blas_depth + 2 > kStackSize)
+    if (keep && tlas_depth + blas_depth + 2 > kStackSize)
         return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack");
 
+    lap("validate");
     // ---- acceleration structure: the caller's topology re-laid out, or (default) a SAH rebuild -----------------------------
     if (s->n_tris > kTriIndexMask) return fail(ctx, MRT_E_UNSUPPORTED, "more than 2^27 triangles");
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     DScene d{};
-    const bool keep = (s->flags & MRT_SCENE_KEEP_TOPOLOGY) != 0;
     const float inf = INFINITY;
     std::vector<DNode> nodes;
     std::vector<uint32_t> tri_map(s->n_tris);      // device triangle index -> caller's triangle index
@@ -932,51 +994,59 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
             if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the traversal stack");
         }
     } else {
-        // emit a built subtree as DNodes; returns the reference its parent stores. leaf_ref(first, count) names a leaf.
-        struct Emit {
-            std::vector<DNode>& out;
-            const mrt_build::Builder& b;
-            std::function<uint32_t(uint32_t, uint32_t)> leaf_ref;
-            decltype(set_child)& set;
-            uint32_t run(int32_t i) {
-                const mrt_build::Node& n = b.nodes[(size_t)i];
-                if (n.left < 0) return leaf_ref(n.first, n.count);
-                const uint32_t me = (uint32_t)out.size();
-                out.push_back(DNode{});
-                uint32_t l = run(n.left), r = run(n.right);
+        // emit a built tree as DNodes in depth-first order (a node's left subtree follows it directly); returns the reference
+        // of the root. leaf_ref(first, count) names a leaf.
+        auto emit_tree = [&](const mrt_build::Tree& t, auto leaf_ref) -> uint32_t {
+            const mrt_build::Node* bn = t.nodes.get();
+            if (bn[t.root].left < 0) {  // the whole set is one leaf: still needs a node to hold its box
                 DNode o{};
-                set(o, 0, l, b.nodes[(size_t)n.left].lo, b.nodes[(size_t)n.left].hi);
-                set(o, 1, r, b.nodes[(size_t)n.right].lo, b.nodes[(size_t)n.right].hi);
-                out[me] = o;
-                return MRT_REF(MRT_PRIM_NODE, me);
-            }
-        };
-        auto emit_tree = [&](mrt_build::Builder& b, int32_t root, std::function<uint32_t(uint32_t, uint32_t)> leaf_ref) -> uint32_t {
-            Emit e{nodes, b, leaf_ref, set_child};
-            if (b.nodes[(size_t)root].left < 0) {  // the whole set is one leaf: still needs a node to hold its box
-                const uint32_t me = (uint32_t)nodes.size();
-                DNode o{};
-                set_child(o, 0, leaf_ref(b.nodes[(size_t)root].first, b.nodes[(size_t)root].count), b.nodes[(size_t)root].lo, b.nodes[(size_t)root].hi);
+                set_child(o, 0, leaf_ref(bn[t.root].first, bn[t.root].count), bn[t.root].lo, bn[t.root].hi);
                 set_child(o, 1, kNone, empty_lo, empty_hi);
                 nodes.push_back(o);
-                return MRT_REF(MRT_PRIM_NODE, me);
+                return MRT_REF(MRT_PRIM_NODE, (uint32_t)nodes.size() - 1);
             }
-            return e.run(root);
+            struct Item { int32_t node; uint32_t parent; int which; };
+            std::vector<Item> st{{t.root, kNone, 0}};
+            uint32_t root_ref = kNone;
+            while (!st.empty()) {
+                const Item it = st.back();
+                st.pop_back();
+                const mrt_build::Node& n = bn[it.node];
+                uint32_t ref;
+                if (n.left < 0) {
+                    ref = leaf_ref(n.first, n.count);
+                } else {
+                    const uint32_t me = (uint32_t)nodes.size();
+                    DNode o{};
+                    set_child(o, 0, kNone, bn[n.left].lo, bn[n.left].hi);  // child references are patched in when the children are emitted
+                    set_child(o, 1, kNone, bn[n.right].lo, bn[n.right].hi);
+                    nodes.push_back(o);
+                    ref = MRT_REF(MRT_PRIM_NODE, me);
+                    st.push_back({n.right, me, 1});
+                    st.push_back({n.left, me, 0});
+                }
+                if (it.parent == kNone) root_ref = ref;
+                else if (it.which == 0) nodes[it.parent].child0 = ref;
+                else nodes[it.parent].child1 = ref;
+            }
+            return root_ref;
         };
         max_blas_depth = 0;
+        nodes.reserve((size_t)s->n_tris + 2 * (size_t)s->n_instances + 2 * (size_t)s->n_spheres + 64);
         for (uint64_t bi = 0; bi < s->n_blas; ++bi) {  // BLAS: SAH, leaves of up to 4 triangles
             const mrt_blas& bl = s->blas[bi];
             std::vector<mrt_build::Prim> prims(bl.n_tris);
-            for (uint32_t i = 0; i < bl.n_tris; ++i) {
-                prims[i].ref = bl.first_tri + i;
-                leaf_bounds(s, MRT_REF(MRT_PRIM_TRIANGLE, bl.first_tri + i), prims[i].lo, prims[i].hi);
-            }
-            mrt_build::Builder b(prims, (int)ctx->opt_leaf_tris, 40, (float)ctx->opt_tri_cost * 0.01f);
-            int32_t root = b.build(0, prims.size(), 0);
-            max_blas_depth = std::max(max_blas_depth, std::max(b.depth_of(root), 1));
+            parallel_for((size_t)bl.n_tris, [&](size_t a, size_t b) {
+                for (size_t i = a; i < b; ++i) {
+                    prims[i].ref = bl.first_tri + (uint32_t)i;
+                    leaf_bounds(s, MRT_REF(MRT_PRIM_TRIANGLE, bl.first_tri + (uint32_t)i), prims[i].lo, prims[i].hi);
+                }
+            });
+            mrt_build::Tree t = mrt_build::build_sah(prims, (int)ctx->opt_leaf_tris, 40, (float)ctx->opt_tri_cost * 0.01f);
+            max_blas_depth = std::max(max_blas_depth, std::max(t.depth, 1));
             for (uint32_t i = 0; i < bl.n_tris; ++i) tri_map[bl.first_tri + i] = prims[i].ref;  // device order = leaf order, inside the BLAS's own range
             const uint32_t base = bl.first_tri;
-            blas_root[bi] = emit_tree(b, root, [base](uint32_t first, uint32_t count) { return MRT_REF(MRT_PRIM_TRIANGLE, base + first) | ((count - 1u) << 27); });
+            blas_root[bi] = emit_tree(t, [base](uint32_t first, uint32_t count) { return MRT_REF(MRT_PRIM_TRIANGLE, base + first) | ((count - 1u) << 27); });
         }
         // TLAS: one SAH tree over every object of the world, one object per leaf -- whether the caller passed World::build_bvh's
         // tree (world.rs:117-122) or the plain object list that World::intersect loops over (world.rs:135-140).
@@ -1000,14 +1070,14 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
             }
         }
         if (!prims.empty()) {
-            mrt_build::Builder b(prims, 1, 28, 4.0f);
-            int32_t root = b.build(0, prims.size(), 0);
-            max_tlas_depth = std::max(b.depth_of(root), 1);
-            const std::vector<mrt_build::Prim>* pp = &prims;
-            device_root = emit_tree(b, root, [pp](uint32_t first, uint32_t) { return (*pp)[first].ref; });
+            mrt_build::Tree t = mrt_build::build_sah(prims, 1, 28, 4.0f);
+            max_tlas_depth = std::max(t.depth, 1);
+            const mrt_build::Prim* pp = prims.data();
+            device_root = emit_tree(t, [pp](uint32_t first, uint32_t) { return pp[first].ref; });
         }
         if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return fail(ctx, MRT_E_UNSUPPORTED, "rebuilt BVH too deep for the traversal stack");
     }
+    lap("build");
     // which triangles can fail Material::alpha_test (geom.rs:567-571): UV'd, and their own material's surface can return alpha 0
     std::vector<int8_t> surf_alpha(s->n_surfaces, -1), mat_alpha(s->n_materials, -1);
     std::function<bool(int32_t)> surface_can_be_transparent = [&](int32_t si) -> bool {
@@ -1039,20 +1109,26 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         spheres[i] = make_float4(s->spheres[i].center[0], s->spheres[i].center[1], s->spheres[i].center[2], s->spheres[i].radius);
         saux[i] = DSphereAux{s->spheres[i].material, s->spheres[i].object_id};
     }
+    for (uint64_t i = 0; i < s->n_materials; ++i) material_can_fail_alpha((int32_t)i);  // fills mat_alpha: the loop below only reads it
     std::vector<DTriVerts> tv(s->n_tris);
-    uint32_t any_alpha = 0;
-    for (uint64_t i = 0; i < s->n_tris; ++i) {
-        const uint32_t orig = tri_map[i];
-        const float* v = s->tri_verts + 9 * (size_t)orig;
-        const mrt_tri_shading& sh = s->tri_shading[orig];
-        uint32_t flags = ((sh.flags & MRT_TRI_HAS_UV) && material_can_fail_alpha(sh.material)) ? kTriAlphaFlag : 0u;
-        any_alpha |= flags;
-        float fw;
-        std::memcpy(&fw, &flags, 4);
-        tv[i].a = make_float4(v[0], v[1], v[2], fw);
-        tv[i].b = make_float4(v[3], v[4], v[5], 0.0f);
-        tv[i].c = make_float4(v[6], v[7], v[8], 0.0f);
-    }
+    std::atomic<uint32_t> any_alpha_acc{0};
+    parallel_for((size_t)s->n_tris, [&](size_t first, size_t last) {
+        uint32_t any = 0;
+        for (size_t i = first; i < last; ++i) {
+            const uint32_t orig = tri_map[i];
+            const float* v = s->tri_verts + 9 * (size_t)orig;
+            const mrt_tri_shading& sh = s->tri_shading[orig];
+            uint32_t flags = ((sh.flags & MRT_TRI_HAS_UV) && mat_alpha[(size_t)sh.material] > 0) ? kTriAlphaFlag : 0u;
+            any |= flags;
+            float fw;
+            std::memcpy(&fw, &flags, 4);
+            tv[i].a = make_float4(v[0], v[1], v[2], fw);
+            tv[i].b = make_float4(v[3], v[4], v[5], 0.0f);
+            tv[i].c = make_float4(v[6], v[7], v[8], 0.0f);
+        }
+        any_alpha_acc |= any;
+    });
+    const uint32_t any_alpha = any_alpha_acc.load();
     std::vector<DInstance> inst(s->n_instances);
     for (uint64_t i = 0; i < s->n_instances; ++i) {
         const mrt_instance& in = s->instances[i];
@@ -1071,6 +1147,7 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         o.object_id = in.object_id;
         o.pad[0] = in.blas;
     }
+    lap("pack");
     int rc;
     if ((rc = upload(ctx, nodes.data(), nodes.size(), &d.nodes))) return rc;
     if ((rc = upload(ctx, spheres.data(), spheres.size(), &d.spheres))) return rc;
@@ -1088,11 +1165,13 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     d.root = device_root;
     d.n_volumes = (uint32_t)s->n_volumes;
     d.has_alpha = any_alpha;
-    d.slow = (any_alpha || s->n_volumes) ? 1u : 0u;
     d.bg = s->background;
     MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
+    lap("copy");
     ctx->scene = d;
     ctx->has_scene = true;
+    ctx->material_kinds = 0;
+    for (uint64_t i = 0; i < s->n_materials; ++i) ctx->material_kinds |= 1u << s->materials[i].kind;
     return MRT_OK;
 }
 
@@ -1134,9 +1213,11 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
-    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths};
-    if (ctx->scene.slow) k_aov<true><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
-    else k_aov<false><<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths, 0u, {}};
+    const unsigned aov_grid = (unsigned)((npix + 127) / 128);
+    if (ctx->scene.has_alpha) k_aov<true, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    else if (ctx->scene.n_volumes) k_aov<false, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
+    else k_aov<false, false><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     AOV_TRY(cudaGetLastError());
     if (albedo) AOV_TRY(cudaMemcpyAsync(albedo, d_alb, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
     if (normal) AOV_TRY(cudaMemcpyAsync(normal, d_nrm, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1169,20 +1250,30 @@ int mrt_accum_reset(mrt_context* ctx, uint32_t w, uint32_t h) {
     return MRT_OK;
 }
 
-static int ensure_pool(mrt_context* ctx, uint64_t total_work) {
+// The shade queues are regions of one buffer, one region per queue kind the scene can produce: the miss queue and the material
+// kinds present in its material table.
+static uint32_t shade_regions(const mrt_context* ctx, uint8_t region[Q_COUNT + 3]) {
+    uint32_t n = 0;
+    for (int k = 0; k < Q_COUNT + 3; ++k) region[k] = 0;
+    region[Q_MISS] = (uint8_t)n++;
+    for (int kind = 0; kind < MRT_MAT_KINDS; ++kind)
+        if (ctx->material_kinds & (1u << kind)) region[Q_FIRST_MAT + kind] = (uint8_t)n++;
+    return n;
+}
+
+static int ensure_pool(mrt_context* ctx, uint64_t total_work, uint32_t regions) {
     uint64_t want = ctx->opt_pool_slots ? ctx->opt_pool_slots : (1ull << 22);
     want = std::min<uint64_t>(want, std::max<uint64_t>((total_work + 1023) / 1024 * 1024, 1024));
-    want = std::min<uint64_t>(want, 1ull << 28);
-    if (ctx->pool.slots == want) return MRT_OK;
+    want = std::min<uint64_t>(want, 1ull << 24);
+    if (ctx->pool.capacity == want && ctx->pool.regions >= regions) return MRT_OK;
     cudaStreamSynchronize(ctx->stream);
     free_pool(ctx);
     Pool& p = ctx->pool;
-    MRT_CUDA(cudaMalloc(&p.slot, want * sizeof(Slot)));
-    MRT_CUDA(cudaMalloc(&p.q_ext[0], want * 4));
-    MRT_CUDA(cudaMalloc(&p.q_ext[1], want * 4));
-    MRT_CUDA(cudaMalloc(&p.q_shade, want * 4 * Q_COUNT));
-    MRT_CUDA(cudaMalloc(&p.free_list, want * 4));
-    p.slots = (uint32_t)want;
+    MRT_CUDA(cudaMalloc(&p.q_ext[0], want * sizeof(RayRec)));
+    MRT_CUDA(cudaMalloc(&p.q_ext[1], want * sizeof(RayRec)));
+    MRT_CUDA(cudaMalloc(&p.q_shade, want * sizeof(HitEntry) * regions));
+    p.capacity = (uint32_t)want;
+    p.regions = regions;
     return MRT_OK;
 }
 
@@ -1200,22 +1291,20 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     st.iterations = st.extend_launches = st.kernel_launches = 0;
     st.render_ms = st.extend_ms = st.shade_ms = st.generate_ms = 0.0f;
     st.scene_bytes = ctx->scene_bytes;
-    if (total == 0) { st.pool_slots = ctx->pool.slots; return MRT_OK; }
-    if ((rc = ensure_pool(ctx, total))) return rc;
-    st.pool_slots = ctx->pool.slots;
+    if (total == 0) { st.pool_slots = ctx->pool.capacity; return MRT_OK; }
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths, 0u, {}};
+    const uint32_t regions = shade_regions(ctx, rp.region);
+    if ((rc = ensure_pool(ctx, total, regions))) return rc;
+    st.pool_slots = ctx->pool.capacity;
     Pool pool = ctx->pool;
-    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths};
+    rp.capacity = pool.capacity;
 
     QueueState init;
     std::memset(&init, 0, sizeof init);
-    init.n_free = pool.slots;
     init.total_work = total;
     ctx->h_q[2] = init;
     MRT_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     MRT_CUDA(cudaMemcpyAsync(ctx->d_q, &ctx->h_q[2], sizeof(QueueState), cudaMemcpyHostToDevice, ctx->stream));
-    k_iota<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(pool.free_list, pool.slots);
-    if (ctx->opt_shade_inorder) k_mark_processed<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(pool);
-    st.kernel_launches++;
 
     std::vector<cudaEvent_t> tev;  // 6 events per iteration when kernel timing is on
     const int kChunk = 8;
@@ -1225,23 +1314,29 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
             cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             if (ctx->opt_time)
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
-            k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, rp.finish_paths);
+            k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, pool.capacity, rp.finish_paths);
+            const int mode = ctx->scene.has_alpha ? 2 : (ctx->scene.n_volumes ? 1 : 0);  // which intersection code the scene needs
             if (rp.finish_paths) {
-                if (ctx->scene.slow) k_finish<true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
-                else k_finish<false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                if (mode == 2) k_finish<true, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                else if (mode == 1) k_finish<false, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                else k_finish<false, false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 st.kernel_launches++;
             }
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[0], ctx->stream));
             k_generate<<<ctx->grid_generate, 256, 0, ctx->stream>>>(ctx->cam, rp, pool, ctx->d_q, cur);
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[1], ctx->stream)); MRT_CUDA(cudaEventRecord(e[2], ctx->stream)); }
-            const bool alpha = ctx->scene.slow != 0;
-            if (ctx->opt_count && alpha) k_extend<true, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
-            else if (ctx->opt_count) k_extend<true, false><<<ctx->grid_extend_count, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
-            else if (alpha) k_extend<false, true><<<ctx->grid_extend_slow, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
-            else k_extend<false, false><<<ctx->grid_extend, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            const int grid = ctx->grid_extend[ctx->opt_count ? 1 : 0][mode];
+            if (ctx->opt_count) {
+                if (mode == 2) k_extend<true, true, true><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+                else if (mode == 1) k_extend<true, false, true><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+                else k_extend<true, false, false><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            } else {
+                if (mode == 2) k_extend<false, true, true><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+                else if (mode == 1) k_extend<false, false, true><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+                else k_extend<false, false, false><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
+            }
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
-            if (ctx->opt_shade_inorder) k_shade_inorder<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
-            else k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+            k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));
             cur ^= 1;
             st.kernel_launches += 4;
@@ -1344,14 +1439,13 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
         case MRT_OPT_COUNT_VISITS: ctx->opt_count = value != 0; return MRT_OK;
         case MRT_OPT_TIME_KERNELS: ctx->opt_time = value != 0; return MRT_OK;
         case MRT_OPT_POOL_SLOTS:
-            if (value != 0 && (value < 1024 || value > (1ull << 28))) return fail(ctx, MRT_E_INVALID, "pool slots out of range [1024, 2^28]");
+            if (value != 0 && (value < 1024 || value > (1ull << 24))) return fail(ctx, MRT_E_INVALID, "pool slots out of range [1024, 2^24]");
             ctx->opt_pool_slots = value / 1024 * 1024;
             return MRT_OK;
         case MRT_OPT_REFILL_LANES:
             if (value < 1 || value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [1, 32]");
             ctx->opt_refill_lanes = (uint32_t)value;
             return MRT_OK;
-        case MRT_OPT_SHADE_INORDER: ctx->opt_shade_inorder = value != 0; return MRT_OK;
         case MRT_OPT_FINISH_PATHS:
             if (value > (1u << 22)) return fail(ctx, MRT_E_INVALID, "finish threshold out of range [0, 2^22]");
             ctx->opt_finish_paths = (uint32_t)value;

@@ -62,7 +62,6 @@ struct DScene {
     uint32_t root;                       // the one root reference (node or single primitive); kNone = empty world
     uint32_t n_volumes;
     uint32_t has_alpha;                  // some triangle carries kTriAlphaFlag
-    uint32_t slow;                       // has_alpha || n_volumes: the SLOW kernel variants (RNG key carried through traversal) are used
     mrt_background bg;
 };
 struct DCamera {
@@ -197,32 +196,35 @@ __device__ __forceinline__ bool triangle_test(const DTriVerts& tv, const Ray& r,
 
 // BoundingBox::hit geom.rs:218-247 for two boxes at once, as a CONSERVATIVE test. NaN handling follows f32::min/max (= fminf/fmaxf).
 // The reference computes (b - o) / d per plane. Here each plane costs one FMA: b * id + ood with id ~ 1/d (MUFU.RCP, <= 1 ulp) and
-// ood = -(o * id), both per ray. Against the reference's value t the result is off by at most 2.5 * 2^-23 * (|t| + |o/d|)
-// (rounding of id, of ood and of the FMA, plus the reference's own two roundings), so the interval is widened by
-// 2^-21 * |t| relatively and by E2 = 2 * 2^-21 * max_axis |o * id| absolutely: the test never rejects a box the reference's
-// test accepts, and nothing computed here reaches a hit record. For d == 0: b * inf - o * inf is +-inf like the reference's
-// x / 0, or NaN (then the axis is ignored, which only accepts more); SlabRay keeps non-finite |o * id| out of E2.
+// ood ~ -(o * id), both per ray. Against the reference's value t the FMA result is off by at most 2.5 * 2^-23 * (|t| + |o * id|)
+// (rounding of id, of o * id and of the FMA, plus the reference's own two roundings). Both terms are covered without extra
+// instructions in the loop: the |o * id| part is folded into the per-ray constants PER AXIS -- the plane that is the near one for
+// this ray's direction sign uses ood - e, the far one ood + e, with e = 2^-21 * |o * id| -- and the |t| part by widening the final
+// interval by 2^-21 relatively. So the test never rejects a box the reference's test accepts, and nothing computed here reaches
+// a hit record. (A single slack for all axes would be wrong in practice: a ray almost parallel to an axis has |o * id| ~ 1e30
+// on that axis, and adding that to the other axes' intervals switches culling off for the whole ray.) For d == 0: b * inf - o * inf
+// is +-inf like the reference's x / 0, or NaN, and then the axis is ignored, which only accepts more.
 struct SlabRay {
-    V3 id;     // ~ 1 / direction
-    V3 ood;    // -(origin * id)
-    float e2;  // absolute slack
+    V3 id;      // ~ 1 / direction
+    V3 ood_lo;  // -(origin * id) -+ e: added to box.min * id
+    V3 ood_hi;  // -(origin * id) +- e: added to box.max * id
 };
 __device__ __forceinline__ void slab2(const DNode& n, const SlabRay& s, float t_min, float t_max, bool& h0, bool& h1, float& n0, float& n1) {
     const float kWiden = 4.76837158203125e-7f;  // 2^-21
-    float a0 = fmaf(n.xy0.x, s.id.x, s.ood.x), b0 = fmaf(n.xy0.y, s.id.x, s.ood.x);
-    float a1 = fmaf(n.xy1.x, s.id.x, s.ood.x), b1 = fmaf(n.xy1.y, s.id.x, s.ood.x);
+    float a0 = fmaf(n.xy0.x, s.id.x, s.ood_lo.x), b0 = fmaf(n.xy0.y, s.id.x, s.ood_hi.x);
+    float a1 = fmaf(n.xy1.x, s.id.x, s.ood_lo.x), b1 = fmaf(n.xy1.y, s.id.x, s.ood_hi.x);
     float tn0 = fmaxf(fminf(a0, b0), t_min), tf0 = fminf(fmaxf(a0, b0), t_max);
     float tn1 = fmaxf(fminf(a1, b1), t_min), tf1 = fminf(fmaxf(a1, b1), t_max);
-    a0 = fmaf(n.xy0.z, s.id.y, s.ood.y); b0 = fmaf(n.xy0.w, s.id.y, s.ood.y);
-    a1 = fmaf(n.xy1.z, s.id.y, s.ood.y); b1 = fmaf(n.xy1.w, s.id.y, s.ood.y);
+    a0 = fmaf(n.xy0.z, s.id.y, s.ood_lo.y); b0 = fmaf(n.xy0.w, s.id.y, s.ood_hi.y);
+    a1 = fmaf(n.xy1.z, s.id.y, s.ood_lo.y); b1 = fmaf(n.xy1.w, s.id.y, s.ood_hi.y);
     tn0 = fmaxf(fminf(a0, b0), tn0); tf0 = fminf(fmaxf(a0, b0), tf0);
     tn1 = fmaxf(fminf(a1, b1), tn1); tf1 = fminf(fmaxf(a1, b1), tf1);
-    a0 = fmaf(n.z01.x, s.id.z, s.ood.z); b0 = fmaf(n.z01.y, s.id.z, s.ood.z);
-    a1 = fmaf(n.z01.z, s.id.z, s.ood.z); b1 = fmaf(n.z01.w, s.id.z, s.ood.z);
+    a0 = fmaf(n.z01.x, s.id.z, s.ood_lo.z); b0 = fmaf(n.z01.y, s.id.z, s.ood_hi.z);
+    a1 = fmaf(n.z01.z, s.id.z, s.ood_lo.z); b1 = fmaf(n.z01.w, s.id.z, s.ood_hi.z);
     tn0 = fmaxf(fminf(a0, b0), tn0); tf0 = fminf(fmaxf(a0, b0), tf0);
     tn1 = fmaxf(fminf(a1, b1), tn1); tf1 = fminf(fmaxf(a1, b1), tf1);
-    h0 = fmaf(-fabsf(tn0), kWiden, tn0) <= fmaf(fabsf(tf0), kWiden, tf0) + s.e2;
-    h1 = fmaf(-fabsf(tn1), kWiden, tn1) <= fmaf(fabsf(tf1), kWiden, tf1) + s.e2;
+    h0 = fmaf(-fabsf(tn0), kWiden, tn0) <= fmaf(fabsf(tf0), kWiden, tf0);
+    h1 = fmaf(-fabsf(tn1), kWiden, tn1) <= fmaf(fabsf(tf1), kWiden, tf1);
     n0 = tn0;
     n1 = tn1;
 }
@@ -264,16 +266,20 @@ __device__ __forceinline__ float rcp_fast(float x) {
     asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void slab_axis(float o, float d, float& id, float& ood_lo, float& ood_hi) {
+    id = rcp_fast(d);
+    const float p = o * id;
+    // inf and NaN products (d == 0) carry no rounding error: no slack (and no NaN from inf * 2^-21 - inf)
+    const float e = (fabsf(p) < 3.0e38f) ? fabsf(p) * 4.76837158203125e-7f : 0.0f;
+    const float se = copysignf(e, id);  // d > 0: box.min is the near plane and gets -e
+    ood_lo = -p - se;
+    ood_hi = -p + se;
+}
 __device__ __forceinline__ SlabRay slab_ray(const Ray& r) {
     SlabRay s;
-    s.id = V3{rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z)};
-    const float px = r.o.x * s.id.x, py = r.o.y * s.id.y, pz = r.o.z * s.id.z;
-    s.ood = V3{-px, -py, -pz};
-    const float big = 3.0e38f;  // inf and NaN products (d == 0) carry no rounding error: they stay out of the slack
-    float m = (fabsf(px) < big) ? fabsf(px) : 0.0f;
-    m = fmaxf(m, (fabsf(py) < big) ? fabsf(py) : 0.0f);
-    m = fmaxf(m, (fabsf(pz) < big) ? fabsf(pz) : 0.0f);
-    s.e2 = m * 9.5367431640625e-7f;  // 2 * 2^-21 * max |o * id|
+    slab_axis(r.o.x, r.d.x, s.id.x, s.ood_lo.x, s.ood_hi.x);
+    slab_axis(r.o.y, r.d.y, s.id.y, s.ood_lo.y, s.ood_hi.y);
+    slab_axis(r.o.z, r.d.z, s.id.z, s.ood_lo.z, s.ood_hi.z);
     return s;
 }
 
@@ -367,9 +373,9 @@ __device__ __forceinline__ void trav_node(const DScene& sc, Traversal& T, uint32
 // Material::alpha_test of the triangle's OWN material at the candidate hit (geom.rs:567-571); defined after the surfaces below
 __device__ bool triangle_alpha_test(const DScene& sc, const DTriVerts& tv, uint32_t tri_dev, const Ray& r, float t, const RngKey& key);
 
-// SLOW = the scene has alpha-tested triangles or volumes: both draw random numbers during intersection (geom.rs:568, :638) and so
-// need the path's RNG key; scenes without them run the variant that carries no key and has neither code path.
-template <bool COUNT, bool SLOW, class W>
+// ALPHA = the scene has alpha-tested triangles, VOLUME = it has volumes: both draw random numbers during intersection (geom.rs:568,
+// :638) and so need the path's RNG key; scenes without them run the variant that carries no key and has neither code path.
+template <bool COUNT, bool ALPHA, bool VOLUME, class W>
 __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32_t* stack, const W& ws, float t_min, const RngKey& key, VisitCounters* cnt) {
     const uint32_t ref = T.ref;
     const uint32_t idx = MRT_REF_INDEX(ref);
@@ -386,7 +392,7 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
                 tv.c = __ldg(&tp->c);
                 float t;
                 if (triangle_test(tv, T.r, t_min, T.best.t, t)) {
-                    if (SLOW && (__float_as_uint(tv.a.w) & kTriAlphaFlag) && !triangle_alpha_test(sc, tv, first + k, T.r, t, key)) continue;  // geom.rs:567-571
+                    if (ALPHA && (__float_as_uint(tv.a.w) & kTriAlphaFlag) && !triangle_alpha_test(sc, tv, first + k, T.r, t, key)) continue;  // geom.rs:567-571
                     T.best = HitRec{t, MRT_REF(MRT_PRIM_TRIANGLE, first + k), T.cur_inst};
                 }
             }
@@ -415,7 +421,7 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
             break;
         }
         case MRT_PRIM_VOLUME: {
-            if (SLOW) {
+            if (VOLUME) {
                 if (COUNT) cnt->volume_tests++;
                 mrt_volume vol = sc.volumes[idx];
                 Rand4 xi = draw4(key, kStreamVolume + idx);
@@ -429,7 +435,7 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
 }
 
 // run a traversal to completion (AOV pass, drain)
-template <bool COUNT, bool SLOW>
+template <bool COUNT, bool ALPHA, bool VOLUME>
 __device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, float t_min, float t_max, const RngKey& key, VisitCounters* cnt) {
     uint32_t stack[kStackSize];
     Traversal T;
@@ -438,7 +444,7 @@ __device__ __forceinline__ HitRec traverse(const DScene& sc, const Ray& world, f
     do {
         while (T.ref != kNone) {
             if (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, t_min, cnt);
-            else trav_leaf<COUNT, SLOW>(sc, T, stack, ws, t_min, key, cnt);
+            else trav_leaf<COUNT, ALPHA, VOLUME>(sc, T, stack, ws, t_min, key, cnt);
         }
     } while (trav_pop(T, stack, ws));
     if (T.best.prim == kNone) T.best.t = t_max;

@@ -75,7 +75,7 @@ def test_aov_cornell(renderer, keep_topology):
     renderer.set_scene(NativeScene(world, camera), keep_topology=keep_topology)
     g = renderer.render_aov(512, 512)
     o = OracleScene(world, camera).render_aov(512, 512)
-    ties, frac = check_aov(g, o, max_ties=64 if keep_topology else None)  # pixel centres exactly on cube-face diagonals
+    ties, frac = check_aov(g, o, max_ties=130 if keep_topology else None)  # 0.05 %: pixel centres exactly on cube-face diagonals
     assert frac == 1.0
 
 
