@@ -341,10 +341,12 @@ def main():
     e2e_s = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = (npix * spp * world_size * len(e2e_t)) / float(e2e_s.item()) / 1e6
     scene_bytes = r.stats()["scene_bytes"] + 76
-    e2e = {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(npix * 16),
-           "ms_per_step": 1e3 * float(e2e_s.item()) / max(len(e2e_t), 1)}
+    e2e = None
+    if e2e_t:
+        e2e_value = (npix * spp * world_size * len(e2e_t)) / float(e2e_s.item()) / 1e6
+        e2e = {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(npix * 16),
+               "ms_per_step": 1e3 * float(e2e_s.item()) / len(e2e_t)}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------------------------------
     cpu = None

@@ -45,7 +45,7 @@ struct QueueState {
     uint32_t ext_cursor;   // persistent-warp fetch cursor of extend
     uint32_t done;
     uint32_t finish_n;     // > 0: the drain has started; k_finish runs these last paths to completion in one launch
-    uint32_t pad0;
+    uint32_t shade_done;   // blocks of k_shade that have finished this iteration (the last one runs advance())
     uint32_t n_shade[Q_COUNT + 3];
     unsigned long long next_work, total_work, gen_base;
     unsigned long long rays, iterations;
@@ -104,20 +104,22 @@ __device__ __forceinline__ void accumulate(long long* accum, uint32_t* nonfinite
     }
 }
 
-__global__ void k_advance(QueueState* q, uint32_t capacity, uint32_t finish_paths) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Bookkeeping between two wavefront iterations (one thread): the paths shade appended become this iteration's continuing
+// rays, the places of ended paths are refilled with the next pixel samples ("regeneration"). Runs in the last block of k_shade
+// to finish (and once, as a kernel of its own, before the first iteration).
+__device__ void advance(QueueState* q, uint32_t capacity, uint32_t finish_paths) {
     q->rays += q->n_ext;
-    uint32_t n_cont = q->n_next;
-    q->n_next = 0;
+    uint32_t n_cont = atomicExch(&q->n_next, 0u);  // the other blocks appended with atomics: read where they wrote (L2), not a cached copy
     for (int k = 0; k < Q_COUNT; ++k) q->n_shade[k] = 0;
     unsigned long long remaining = q->total_work - q->next_work;
-    uint32_t n_new = (uint32_t)min((unsigned long long)(capacity - n_cont), remaining);  // regeneration: refill the places of ended paths
+    uint32_t n_new = (uint32_t)min((unsigned long long)(capacity - n_cont), remaining);
     q->gen_base = q->next_work;
     q->next_work += n_new;
     q->finish_n = 0;
     if (remaining == 0 && n_cont > 0 && n_cont <= finish_paths) {
         // the job is draining: no samples left to regenerate and only a few paths alive. Instead of up to max_depth more
         // wavefront iterations over a nearly empty queue, k_finish runs each remaining path to its end in this iteration.
+        // (finish_paths is 0 on iterations whose launch sequence has no k_finish.)
         q->finish_n = n_cont;
         n_cont = 0;
     }
@@ -127,6 +129,9 @@ __global__ void k_advance(QueueState* q, uint32_t capacity, uint32_t finish_path
     q->ext_cursor = 0;
     q->done = (n_cont + n_new == 0 && q->finish_n == 0) ? 1u : 0u;
     if (n_cont + n_new + q->finish_n) q->iterations++;
+}
+__global__ void k_advance(QueueState* q, uint32_t capacity, uint32_t finish_paths) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) advance(q, capacity, finish_paths);
 }
 
 // Camera::ray world.rs:53-63 with the pixel jitter of main.rs:258-259 (jitter == false: pixel centres, main.rs:189-190)
@@ -329,7 +334,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // with coalesced 128-bit loads -- the entries of its next turn are prefetched into L2 meanwhile -- and appends the scattered
 // rays of the surviving paths to the next extend queue with one atomic per warp.
 __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
-                                                                            QueueState* q, int cur, long long* accum, uint32_t* nonfinite) {
+                                                                            QueueState* q, int cur, long long* accum, uint32_t* nonfinite,
+                                                                            uint32_t next_finish_paths) {
     RayRec* __restrict__ q_next = pool.q_ext[cur ^ 1];
     const uint32_t lane = lane_id(), lt_mask = (1u << lane) - 1u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -369,6 +375,19 @@ __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(con
                 }
             }
         }
+    }
+    // the last block to get here closes the iteration (saves a one-thread kernel launch per iteration)
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // this block's appends to n_next are visible before its ticket
+        s_last = atomicAdd(&q->shade_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        q->shade_done = 0;
+        advance(q, pool.capacity, next_finish_paths);
     }
 }
 
@@ -1309,14 +1328,18 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     std::vector<cudaEvent_t> tev;  // 6 events per iteration when kernel timing is on
     const int kChunk = 8;
     int cur = 0;
+    const int mode = ctx->scene.has_alpha ? 2 : (ctx->scene.n_volumes ? 1 : 0);  // which intersection code the scene needs
+    // Per iteration: generate, extend, shade (whose last block also does the bookkeeping for the next iteration). The drain
+    // kernel k_finish is launched once per chunk, in front of its first iteration; only the advance() that precedes such an
+    // iteration may hand paths to it (finish_paths != 0).
+    k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, pool.capacity, rp.finish_paths);
+    st.kernel_launches++;
     auto launch_chunk = [&](int slot) -> int {
         for (int it = 0; it < kChunk; ++it) {
             cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             if (ctx->opt_time)
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
-            k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, pool.capacity, rp.finish_paths);
-            const int mode = ctx->scene.has_alpha ? 2 : (ctx->scene.n_volumes ? 1 : 0);  // which intersection code the scene needs
-            if (rp.finish_paths) {
+            if (it == 0 && rp.finish_paths) {
                 if (mode == 2) k_finish<true, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 else if (mode == 1) k_finish<false, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 else k_finish<false, false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
@@ -1336,10 +1359,11 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
                 else k_extend<false, false, false><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             }
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
-            k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+            const uint32_t next_finish = (it == kChunk - 1) ? rp.finish_paths : 0u;  // the next iteration opens a chunk: k_finish runs before it
+            k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite, next_finish);
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));
             cur ^= 1;
-            st.kernel_launches += 4;
+            st.kernel_launches += 3;
             st.extend_launches += 1;
         }
         MRT_CUDA(cudaGetLastError());
