@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bvh", default="default", choices=["default", "sah"],
+                    help="default: meshes of >= 16384 triangles get their BLAS built on the GPU (LBVH, milliseconds); sah: the host's SAH builder for every mesh")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules; using 3", file=sys.stderr)
@@ -218,6 +220,8 @@ def main():
 
     stream = torch.cuda.Stream(device=dev)
     r = Renderer(local_rank, stream=stream.cuda_stream)
+    if args.bvh == "sah":
+        r.set_option(Renderer.OPT_DEVICE_BUILD, 0)
     r.set_scene(host)
     npix = w * h
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -370,7 +374,8 @@ def main():
             "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "spp_per_gpu_per_step": spp, "max_depth": 50,
                        "partition": f"samples per pixel split over {world_size} rank(s), one NCCL int64 sum-reduce per step" if world_size > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write); the ray / shade queues of one iteration (>= 460 MB at 4M paths in flight) also exceed the 126 MB L2",
-                       "scene_build_s": build_s, "rays_per_path": rays / paths},
+                       "scene_build_s": build_s, "rays_per_path": rays / paths,
+                       "bvh": "host SAH for every mesh" if args.bvh == "sah" else "GPU LBVH for meshes of >= 16384 triangles, host SAH otherwise"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

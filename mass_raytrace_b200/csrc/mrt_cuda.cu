@@ -32,6 +32,7 @@
 #include "mrt_bvh_build.h"
 #include "mrt_debug.h"
 #include "mrt_device.cuh"
+#include "mrt_lbvh.cuh"
 
 namespace mrt {
 
@@ -572,6 +573,10 @@ struct mrt_context {
     uint64_t opt_pool_slots = 0;
     uint32_t opt_finish_paths = 65536;
     uint32_t opt_leaf_tris = 4, opt_tri_cost = 100;
+    bool opt_device_build = true;   // MRT_OPT_DEVICE_BUILD: big meshes get an LBVH built on the GPU instead of the host's SAH tree
+    DevBuf build_scratch;           // raw vertices + work arrays of the GPU builder (grow-only)
+    int* d_depths = nullptr;        // tree depth of each GPU-built BLAS
+    int* h_depths = nullptr;        // pinned
     uint32_t opt_refill_lanes = kRefillLanes;
     mrt_stats stats{};
     int grid_extend[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [count visits][0 plain, 1 volumes, 2 alpha-tested triangles (+ volumes)]
@@ -622,23 +627,34 @@ static void parallel_for(size_t n, Fn fn) {
     for (auto& t : th) t.join();
 }
 
-template <class T>
-static int upload(mrt_context* ctx, const T* src, size_t n, const T** dst) {
-    *dst = nullptr;
-    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+static int grow(mrt_context* ctx, mrt_context::DevBuf& buf, size_t bytes) {
+    if (buf.cap >= bytes) return MRT_OK;
+    if (buf.p) cudaFree(buf.p);
+    buf = mrt_context::DevBuf{};
+    const size_t cap = bytes + bytes / 8;  // a little headroom: an animated scene rarely keeps its exact size
+    MRT_CUDA(cudaMalloc(&buf.p, cap));
+    buf.cap = cap;
+    return MRT_OK;
+}
+
+// next array of the scene arena, `bytes` long
+static int arena_alloc(mrt_context* ctx, size_t bytes, void** out) {
+    *out = nullptr;
+    bytes = std::max<size_t>(bytes, 16);
     if (ctx->scene_buf_next >= ctx->scene_bufs.size()) ctx->scene_bufs.emplace_back();
     mrt_context::DevBuf& buf = ctx->scene_bufs[ctx->scene_buf_next++];
-    if (buf.cap < bytes) {
-        if (buf.p) cudaFree(buf.p);
-        buf = mrt_context::DevBuf{};
-        const size_t cap = bytes + bytes / 8;  // a little headroom: an animated scene rarely keeps its exact size
-        MRT_CUDA(cudaMalloc(&buf.p, cap));
-        buf.cap = cap;
-    }
+    int rc = grow(ctx, buf, bytes);
+    if (rc) return rc;
     ctx->scene_bytes += bytes;
-    const char* from = reinterpret_cast<const char*>(src);
-    for (size_t off = 0; off < n * sizeof(T); off += kStageChunk) {
-        const size_t len = std::min(kStageChunk, n * sizeof(T) - off);
+    *out = buf.p;
+    return MRT_OK;
+}
+
+// host -> device through the two pinned staging chunks: the memcpy into one chunk overlaps the DMA out of the other
+static int stage_copy(mrt_context* ctx, void* dst, const void* src, size_t bytes) {
+    const char* from = static_cast<const char*>(src);
+    for (size_t off = 0; off < bytes; off += kStageChunk) {
+        const size_t len = std::min(kStageChunk, bytes - off);
         const int k = ctx->stage_next;
         ctx->stage_next ^= 1;
         if (!ctx->stage[k]) {
@@ -648,10 +664,19 @@ static int upload(mrt_context* ctx, const T* src, size_t n, const T** dst) {
             MRT_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));  // the DMA that last read this chunk has finished
         }
         parallel_memcpy(ctx->stage[k], from + off, len);
-        MRT_CUDA(cudaMemcpyAsync(static_cast<char*>(buf.p) + off, ctx->stage[k], len, cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->stage[k], len, cudaMemcpyHostToDevice, ctx->stream));
         MRT_CUDA(cudaEventRecord(ctx->stage_ev[k], ctx->stream));
     }
-    *dst = static_cast<const T*>(buf.p);
+    return MRT_OK;
+}
+
+template <class T>
+static int upload(mrt_context* ctx, const T* src, size_t n, const T** dst) {
+    void* p = nullptr;
+    int rc = arena_alloc(ctx, n * sizeof(T), &p);
+    if (rc) return rc;
+    if (n && (rc = stage_copy(ctx, p, src, n * sizeof(T)))) return rc;
+    *dst = static_cast<const T*>(p);
     return MRT_OK;
 }
 
@@ -664,6 +689,11 @@ static void free_scene(mrt_context* ctx) {
 static void release_scene_arena(mrt_context* ctx) {
     for (auto& b : ctx->scene_bufs) cudaFree(b.p);
     ctx->scene_bufs.clear();
+    cudaFree(ctx->build_scratch.p);
+    ctx->build_scratch = mrt_context::DevBuf{};
+    cudaFree(ctx->d_depths);
+    if (ctx->h_depths) cudaFreeHost(ctx->h_depths);
+    ctx->d_depths = ctx->h_depths = nullptr;
     for (int k = 0; k < 2; ++k) {
         if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
         if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
@@ -840,8 +870,19 @@ static int subtree_depth(const mrt_scene_desc* s, uint32_t root, bool tlas, std:
     return best;
 }
 
+constexpr int kRetryOnHost = 1;  // internal: the GPU-built tree is too deep for the traversal stack
+constexpr uint32_t kDeviceBuildMin = 16384, kDeviceBuildMaxMeshes = 1024;
+
+static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device);
+
 int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if (!ctx) return MRT_E_INVALID;
+    int rc = scene_upload_impl(ctx, s, ctx->opt_device_build);
+    if (rc == kRetryOnHost) rc = scene_upload_impl(ctx, s, false);
+    return rc;
+}
+
+static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device) {
     if (!s) return fail(ctx, MRT_E_INVALID, "scene is NULL");
     if (s->abi_version != MRT_ABI_VERSION) return fail(ctx, MRT_E_INVALID, "mrt_scene_desc.abi_version mismatch");
     MRT_CUDA(cudaSetDevice(ctx->device));
@@ -956,6 +997,7 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     const float empty_lo[3] = {inf, inf, inf}, empty_hi[3] = {-inf, -inf, -inf};
     int max_tlas_depth = tlas_depth, max_blas_depth = blas_depth;
     uint32_t device_root = kNone;  // stays kNone for an empty world
+    std::vector<uint32_t> device_meshes;  // BLAS indices the GPU builds
     if (keep) {
         nodes.resize(s->n_nodes);
         for (uint64_t i = 0; i < s->n_nodes; ++i) {
@@ -1054,6 +1096,10 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         nodes.reserve((size_t)s->n_tris + 2 * (size_t)s->n_instances + 2 * (size_t)s->n_spheres + 64);
         for (uint64_t bi = 0; bi < s->n_blas; ++bi) {  // BLAS: SAH, leaves of up to 4 triangles
             const mrt_blas& bl = s->blas[bi];
+            if (allow_device && bl.n_tris >= kDeviceBuildMin && device_meshes.size() < kDeviceBuildMaxMeshes) {
+                device_meshes.push_back((uint32_t)bi);  // built on the GPU after the upload (mrt_lbvh.cuh); its root is set below
+                continue;
+            }
             std::vector<mrt_build::Prim> prims(bl.n_tris);
             parallel_for((size_t)bl.n_tris, [&](size_t a, size_t b) {
                 for (size_t i = a; i < b; ++i) {
@@ -1096,6 +1142,15 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         }
         if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return fail(ctx, MRT_E_UNSUPPORTED, "rebuilt BVH too deep for the traversal stack");
     }
+    // GPU-built meshes: their nodes follow the host-built ones in the node array, root first
+    std::vector<uint32_t> device_node_base(device_meshes.size());
+    size_t n_nodes_total = nodes.size();
+    for (size_t k = 0; k < device_meshes.size(); ++k) {
+        device_node_base[k] = (uint32_t)n_nodes_total;
+        blas_root[device_meshes[k]] = MRT_REF(MRT_PRIM_NODE, (uint32_t)n_nodes_total);
+        n_nodes_total += s->blas[device_meshes[k]].n_tris - 1;
+    }
+    if (n_nodes_total >= (1ull << 29)) return fail(ctx, MRT_E_INVALID, "too many BVH nodes for 29-bit references");
     lap("build");
     // which triangles can fail Material::alpha_test (geom.rs:567-571): UV'd, and their own material's surface can return alpha 0
     std::vector<int8_t> surf_alpha(s->n_surfaces, -1), mat_alpha(s->n_materials, -1);
@@ -1129,25 +1184,36 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
         saux[i] = DSphereAux{s->spheres[i].material, s->spheres[i].object_id};
     }
     for (uint64_t i = 0; i < s->n_materials; ++i) material_can_fail_alpha((int32_t)i);  // fills mat_alpha: the loop below only reads it
-    std::vector<DTriVerts> tv(s->n_tris);
+    std::vector<uint8_t> on_device(s->n_blas, 0);
+    for (uint32_t bi : device_meshes) on_device[bi] = 1;
+    std::unique_ptr<DTriVerts[]> tv(new DTriVerts[std::max<size_t>((size_t)s->n_tris, 1)]);  // untouched where the GPU fills in
     std::atomic<uint32_t> any_alpha_acc{0};
-    parallel_for((size_t)s->n_tris, [&](size_t first, size_t last) {
+    parallel_for((size_t)s->n_tris, [&](size_t first, size_t last) {  // alpha-tested triangles anywhere in the scene?
         uint32_t any = 0;
         for (size_t i = first; i < last; ++i) {
-            const uint32_t orig = tri_map[i];
-            const float* v = s->tri_verts + 9 * (size_t)orig;
-            const mrt_tri_shading& sh = s->tri_shading[orig];
-            uint32_t flags = ((sh.flags & MRT_TRI_HAS_UV) && mat_alpha[(size_t)sh.material] > 0) ? kTriAlphaFlag : 0u;
-            any |= flags;
-            float fw;
-            std::memcpy(&fw, &flags, 4);
-            tv[i].a = make_float4(v[0], v[1], v[2], fw);
-            tv[i].b = make_float4(v[3], v[4], v[5], 0.0f);
-            tv[i].c = make_float4(v[6], v[7], v[8], 0.0f);
+            const mrt_tri_shading& sh = s->tri_shading[i];
+            if ((sh.flags & MRT_TRI_HAS_UV) && mat_alpha[(size_t)sh.material] > 0) any = kTriAlphaFlag;
         }
         any_alpha_acc |= any;
     });
     const uint32_t any_alpha = any_alpha_acc.load();
+    for (uint64_t bi = 0; bi < s->n_blas; ++bi) {
+        if (on_device[bi]) continue;
+        const size_t base = s->blas[bi].first_tri;
+        parallel_for((size_t)s->blas[bi].n_tris, [&](size_t first, size_t last) {
+            for (size_t i = base + first; i < base + last; ++i) {
+                const uint32_t orig = tri_map[i];
+                const float* v = s->tri_verts + 9 * (size_t)orig;
+                const mrt_tri_shading& sh = s->tri_shading[orig];
+                uint32_t flags = ((sh.flags & MRT_TRI_HAS_UV) && mat_alpha[(size_t)sh.material] > 0) ? kTriAlphaFlag : 0u;
+                float fw;
+                std::memcpy(&fw, &flags, 4);
+                tv[i].a = make_float4(v[0], v[1], v[2], fw);
+                tv[i].b = make_float4(v[3], v[4], v[5], 0.0f);
+                tv[i].c = make_float4(v[6], v[7], v[8], 0.0f);
+            }
+        });
+    }
     std::vector<DInstance> inst(s->n_instances);
     for (uint64_t i = 0; i < s->n_instances; ++i) {
         const mrt_instance& in = s->instances[i];
@@ -1168,11 +1234,24 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     }
     lap("pack");
     int rc;
-    if ((rc = upload(ctx, nodes.data(), nodes.size(), &d.nodes))) return rc;
+    DNode* d_nodes = nullptr;
+    DTriVerts* d_tv = nullptr;
+    uint32_t* d_tri_map = nullptr;
+    if ((rc = arena_alloc(ctx, n_nodes_total * sizeof(DNode), reinterpret_cast<void**>(&d_nodes)))) return rc;
+    if (!nodes.empty() && (rc = stage_copy(ctx, d_nodes, nodes.data(), nodes.size() * sizeof(DNode)))) return rc;
     if ((rc = upload(ctx, spheres.data(), spheres.size(), &d.spheres))) return rc;
     if ((rc = upload(ctx, saux.data(), saux.size(), &d.sphere_aux))) return rc;
-    if ((rc = upload(ctx, tv.data(), tv.size(), &d.tri_verts))) return rc;
-    if ((rc = upload(ctx, tri_map.data(), tri_map.size(), &d.tri_map))) return rc;
+    if ((rc = arena_alloc(ctx, (size_t)s->n_tris * sizeof(DTriVerts), reinterpret_cast<void**>(&d_tv)))) return rc;
+    if ((rc = arena_alloc(ctx, (size_t)s->n_tris * sizeof(uint32_t), reinterpret_cast<void**>(&d_tri_map)))) return rc;
+    for (uint64_t bi = 0; bi < s->n_blas; ++bi) {  // host-built meshes: their triangle ranges; the GPU builder writes the others
+        if (on_device[bi]) continue;
+        const size_t base = s->blas[bi].first_tri, n = s->blas[bi].n_tris;
+        if ((rc = stage_copy(ctx, d_tv + base, tv.get() + base, n * sizeof(DTriVerts)))) return rc;
+        if ((rc = stage_copy(ctx, d_tri_map + base, tri_map.data() + base, n * sizeof(uint32_t)))) return rc;
+    }
+    d.nodes = d_nodes;
+    d.tri_verts = d_tv;
+    d.tri_map = d_tri_map;
     if ((rc = upload(ctx, s->tri_shading, (size_t)s->n_tris, &d.tri_shading))) return rc;
     if ((rc = upload(ctx, inst.data(), inst.size(), &d.instances))) return rc;
     if ((rc = upload(ctx, s->blas, (size_t)s->n_blas, &d.blas))) return rc;
@@ -1185,8 +1264,39 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     d.n_volumes = (uint32_t)s->n_volumes;
     d.has_alpha = any_alpha;
     d.bg = s->background;
-    MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
     lap("copy");
+    if (!device_meshes.empty()) {  // ---- build the big meshes on the GPU, one after the other on the upload stream --------
+        const uint8_t* d_mat_alpha = nullptr;
+        std::vector<uint8_t> ma(s->n_materials);
+        for (uint64_t i = 0; i < s->n_materials; ++i) ma[i] = mat_alpha[i] > 0 ? 1 : 0;
+        if ((rc = upload(ctx, ma.data(), ma.size(), &d_mat_alpha))) return rc;
+        if (!ctx->d_depths) {
+            MRT_CUDA(cudaMalloc(&ctx->d_depths, kDeviceBuildMaxMeshes * sizeof(int)));
+            MRT_CUDA(cudaMallocHost(&ctx->h_depths, kDeviceBuildMaxMeshes * sizeof(int)));
+        }
+        size_t need = 0;
+        for (uint32_t bi : device_meshes) {
+            const size_t n = s->blas[bi].n_tris;
+            need = std::max(need, (n * 36 + 255) / 256 * 256 + lbvh::scratch_bytes(n, lbvh::cub_temp_bytes(n)));
+        }
+        if ((rc = grow(ctx, ctx->build_scratch, need))) return rc;
+        for (size_t k = 0; k < device_meshes.size(); ++k) {
+            const mrt_blas& bl = s->blas[device_meshes[k]];
+            const size_t n = bl.n_tris, raw_bytes = (n * 36 + 255) / 256 * 256;
+            float* d_raw = static_cast<float*>(ctx->build_scratch.p);
+            if ((rc = stage_copy(ctx, d_raw, s->tri_verts + 9 * (size_t)bl.first_tri, n * 36))) return rc;
+            lbvh::Scratch sc = lbvh::carve(static_cast<char*>(ctx->build_scratch.p) + raw_bytes, n, lbvh::cub_temp_bytes(n));
+            MRT_CUDA(lbvh::build(ctx->stream, sc, d_raw, (uint32_t)n, d.tri_shading, d_mat_alpha, bl.first_tri, d_nodes, device_node_base[k], d_tv, d_tri_map,
+                                 ctx->d_depths + k));
+        }
+        MRT_CUDA(cudaMemcpyAsync(ctx->h_depths, ctx->d_depths, device_meshes.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
+    if (!device_meshes.empty()) {
+        for (size_t k = 0; k < device_meshes.size(); ++k) max_blas_depth = std::max(max_blas_depth, ctx->h_depths[k]);
+        lap("gpu build");
+        if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return kRetryOnHost;  // pathological Morton order: let the host's SAH builder do it
+    }
     ctx->scene = d;
     ctx->has_scene = true;
     ctx->material_kinds = 0;
@@ -1474,6 +1584,7 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             if (value > (1u << 22)) return fail(ctx, MRT_E_INVALID, "finish threshold out of range [0, 2^22]");
             ctx->opt_finish_paths = (uint32_t)value;
             return MRT_OK;
+        case MRT_OPT_DEVICE_BUILD: ctx->opt_device_build = value != 0; return MRT_OK;
         case MRT_OPT_BVH_LEAF_TRIS:
             if (value < 1 || value > 4) return fail(ctx, MRT_E_INVALID, "leaf size out of range [1, 4]");
             ctx->opt_leaf_tris = (uint32_t)value;

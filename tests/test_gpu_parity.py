@@ -180,11 +180,16 @@ def test_aov_full_size_million_triangle_mesh(renderer, tmp_mesh_dir):
     world, camera = scenes.lucy_layout(path, md, grid=0)
     host = NativeScene(world, camera)
     assert host.desc().contents.n_tris == (1 << 20) + 12
-    renderer.set_scene(host)
-    g = renderer.render_aov(1920, 1080)
     o = OracleScene(world, camera).render_aov(1920, 1080)
-    ties, frac = check_aov(g, o)
-    assert (g["tri"] != NONE).mean() > 0.2
+    try:
+        for device_build in (1, 0):  # the GPU's LBVH (default for a mesh this size) and the host's SAH tree
+            renderer.set_option(renderer.OPT_DEVICE_BUILD, device_build)
+            renderer.set_scene(host)
+            g = renderer.render_aov(1920, 1080)
+            ties, frac = check_aov(g, o)
+            assert (g["tri"] != NONE).mean() > 0.2
+    finally:
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -642,3 +647,43 @@ def test_obj_scene_textured_and_alpha(renderer, tmp_path):
     lum = lambda a: float((a @ Y).mean()) / spp
     assert abs(lum(rgb) - lum(orgb)) < 0.02 * lum(orgb)
     assert abs(b.mean() - ob.mean()) < 0.02 * ob.mean()
+
+
+def test_device_built_bvh(renderer, mesh_ply):
+    """MRT_OPT_DEVICE_BUILD (on by default): meshes of >= 16384 triangles get their BLAS built on the GPU (Morton-order LBVH, mrt_lbvh.cuh). A closest
+    hit does not depend on the tree, so primary rays must match the oracle exactly as with the host's SAH tree -- instanced meshes,
+    and a UV mesh whose texture alpha punches holes (the builder's gather kernel sets the alpha flag per triangle)."""
+    path, md, n = mesh_ply
+    world, camera = scenes.lucy_layout(path, md, grid=2)  # 25 instances of one 65,536-triangle mesh
+    o = OracleScene(world, camera).render_aov(640, 360)
+    try:
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)
+        renderer.set_scene(NativeScene(world, camera))
+        g = renderer.render_aov(640, 360)
+        check_aov(g, o)
+        assert (g["tri"] != NONE).mean() > 0.3
+        rgb_dev, b_dev, _ = renderer.render(160, 90, 16, 50, seed=9)
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 0)
+        renderer.set_scene(NativeScene(world, camera))
+        rgb_host, b_host, _ = renderer.render(160, 90, 16, 50, seed=9)
+        # same samples, same hits (up to exact-t ties on shared edges): the two images agree almost everywhere bit for bit
+        assert (b_dev == b_host).mean() > 0.999 and np.abs(rgb_dev - rgb_host).max(-1).mean() < 1e-3
+
+        rs = np.random.RandomState(2)
+        px = rs.randint(0, 256, (16, 16, 4)).astype(np.uint8)
+        px[..., 3] = 255
+        px[:, (np.arange(16) // 4) % 2 == 0, 3] = 0
+        w = World(SkyBackground())
+        w.add(Model(scenes.uv_sphere_triangles((0.0, 1.0, 0.0), 1.0, 192, 96, material=Lambertian(Texture(px, WRAP_CLAMP)))))  # 36,864 triangles
+        w.add(Sphere(Lambertian(SolidColor((0.8, 0.2, 0.2, 1))), V3(0, -1000, 0), 1000.0))
+        w.build_bvh()
+        cam = Camera(35.0, V3(0, 1.5, 5), V3(0, 1, 0), V3(0, 1, 0), 1.5, 0.0, 5.0)
+        o2 = OracleScene(w, cam).render_aov(360, 240)
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)
+        renderer.set_scene(NativeScene(w, cam))
+        g2 = renderer.render_aov(360, 240)
+        check_aov(g2, o2, albedo_exact=False)
+        near = g2["t"][g2["object"] == 0].min()
+        assert ((g2["object"] == 0) & (g2["t"] > 1.3 * near)).sum() > 1000  # rays that went through a hole and hit the far inside of the sphere
+    finally:
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)
