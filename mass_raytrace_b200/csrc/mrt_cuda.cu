@@ -120,7 +120,6 @@ __device__ void advance(QueueState* q, uint32_t capacity, uint32_t finish_paths)
     if (remaining == 0 && n_cont > 0 && n_cont <= finish_paths) {
         // the job is draining: no samples left to regenerate and only a few paths alive. Instead of up to max_depth more
         // wavefront iterations over a nearly empty queue, k_finish runs each remaining path to its end in this iteration.
-        // (finish_paths is 0 on iterations whose launch sequence has no k_finish.)
         q->finish_n = n_cont;
         n_cont = 0;
     }
@@ -1439,9 +1438,9 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     const int kChunk = 8;
     int cur = 0;
     const int mode = ctx->scene.has_alpha ? 2 : (ctx->scene.n_volumes ? 1 : 0);  // which intersection code the scene needs
-    // Per iteration: generate, extend, shade (whose last block also does the bookkeeping for the next iteration). The drain
-    // kernel k_finish is launched once per chunk, in front of its first iteration; only the advance() that precedes such an
-    // iteration may hand paths to it (finish_paths != 0).
+    // Per iteration: [finish,] generate, extend, shade (whose last block also does the bookkeeping for the next iteration). The
+    // drain kernel k_finish returns at once unless advance() has handed it the last paths of the job; launching it in every
+    // iteration (2.5 us) ends a job as soon as few enough paths are alive, which matters for renders of a few samples per pixel.
     k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, pool.capacity, rp.finish_paths);
     st.kernel_launches++;
     auto launch_chunk = [&](int slot) -> int {
@@ -1449,7 +1448,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
             cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             if (ctx->opt_time)
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
-            if (it == 0 && rp.finish_paths) {
+            if (rp.finish_paths) {
                 if (mode == 2) k_finish<true, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 else if (mode == 1) k_finish<false, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 else k_finish<false, false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
@@ -1469,8 +1468,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
                 else k_extend<false, false, false><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             }
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
-            const uint32_t next_finish = (it == kChunk - 1) ? rp.finish_paths : 0u;  // the next iteration opens a chunk: k_finish runs before it
-            k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite, next_finish);
+            k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite, rp.finish_paths);
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));
             cur ^= 1;
             st.kernel_launches += 3;
