@@ -261,7 +261,8 @@ enum {
     MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */
     MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
     MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^24 (0 = default 2^22) */
-    MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes once at least this many of a warp's 32 lanes are idle (default 32: whole batches) */
+    MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes of continuing rays once this many of a warp's 32 lanes are idle;
+                                 0 (default) = by scene: 32 (whole batches), or 20 when a mesh's tree is deep */
     MRT_OPT_DEVICE_BUILD = 11, /* mrt_scene_upload builds the BLAS of meshes of >= 16384 triangles ON THE GPU (linear BVH, ~3 ms per million
                                   triangles; default 1). 0: the host's SAH builder for every mesh (0.25 s per million triangles, ~13 % faster
                                   traversal): worth it for renders of thousands of samples per pixel */

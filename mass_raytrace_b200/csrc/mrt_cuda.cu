@@ -169,14 +169,18 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
 // ("chain": all lanes run the node loop together, then the leaf code of each primitive kind present). When at least
 // `refill_lanes` lanes of a warp have finished, the warp commits their hits -- hit record, then one __match_any_sync + one
 // atomicAdd per (warp, material kind) to append to the material-sorted shade queues -- and refills those lanes with one
-// atomicAdd on the queue cursor. Measured on B200 (profiles/README.md): the best threshold is 32, i.e. a warp takes 32
-// consecutive queue entries, runs them to the end and commits them together. Consecutive entries are neighbouring pixels or
-// paths shaded together, so they start in phase (all at the root, then all a few nodes from their next leaf); refilling single
-// lanes early -- even for the price of a few shared-memory loads from a prefetched ring -- mixes rays that need five node
-// visits with rays that need one and costs more warp instructions than the idle lanes save.
+// atomicAdd on the queue cursor. Measured on B200 (profiles/README.md): on scenes whose trees are shallow (spheres, boxes, small
+// meshes, however many instances) the best threshold is 32, i.e. a warp takes 32 consecutive queue entries, runs them to the
+// end and commits them together. Consecutive entries are neighbouring pixels or paths shaded together, so they start in phase
+// (all at the root, then all a few nodes from their next leaf); refilling lanes early -- even for the price of a few
+// shared-memory loads from a prefetched ring -- mixes rays that need five node visits with rays that need one and costs more
+// warp instructions than the idle lanes save. Under a deep BLAS (a mesh of tens of thousands of triangles or more) ray lengths
+// vary so much that the idle tail dominates (5-7 of 32 lanes active on bounce rays): there continuing rays are refilled at 20
+// idle lanes (-7 % k_extend time on the 1 M- and 10 M-triangle scenes); camera rays always run as whole batches.
 // Leaving an instance is free: stack entries pushed before the instance was entered lie below inst_base, and popping one
 // restores the world-space ray from shared memory (no sentinel entries).
-constexpr uint32_t kRefillLanes = 32;  // default; MRT_OPT_REFILL_LANES overrides it
+constexpr uint32_t kRefillLanes = 32, kRefillLanesDeep = 20;  // defaults (shallow / deep BLAS); MRT_OPT_REFILL_LANES overrides them
+constexpr int kDeepBlas = 12;                                 // inner-node levels from which a BLAS counts as deep
 constexpr int kExtendThreads = 128;
 
 template <bool COUNT, bool ALPHA, bool VOLUME>
@@ -193,7 +197,10 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
     const float inf = __int_as_float(0x7f800000);
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t refill_lanes = rp.refill_lanes;
+    // refill threshold: new camera rays (the tail of the queue, entries >= n_cont) are coherent and start in phase, so a warp
+    // always runs a batch of them to the end (32); continuing rays use rp.refill_lanes
+    const uint32_t n_cont = q->n_cont;
+    uint32_t refill_lanes = rp.refill_lanes;
     VisitCounters cnt{0, 0, 0, 0, 0};
     uint32_t stack[kStackSize];
     Traversal T;
@@ -238,6 +245,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(&q->ext_cursor, want);
                 base = __shfl_sync(0xffffffffu, base, leader);
+                if (base + want > n_cont) refill_lanes = 32u;
                 const uint32_t i = base + __popc(idle & lt_mask);
                 if (!active && i < n) {
                     const RayRec* rec = &queue[i];
@@ -576,7 +584,8 @@ struct mrt_context {
     DevBuf build_scratch;           // raw vertices + work arrays of the GPU builder (grow-only)
     int* d_depths = nullptr;        // tree depth of each GPU-built BLAS
     int* h_depths = nullptr;        // pinned
-    uint32_t opt_refill_lanes = kRefillLanes;
+    uint32_t opt_refill_lanes = 0;  // 0 = by scene: kRefillLanesDeep under a deep BLAS, else kRefillLanes
+    uint32_t auto_refill_lanes = kRefillLanes;
     mrt_stats stats{};
     int grid_extend[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [count visits][0 plain, 1 volumes, 2 alpha-tested triangles (+ volumes)]
     int grid_shade = 0, grid_generate = 0;
@@ -1298,6 +1307,7 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     }
     ctx->scene = d;
     ctx->has_scene = true;
+    ctx->auto_refill_lanes = max_blas_depth >= kDeepBlas ? kRefillLanesDeep : kRefillLanes;
     ctx->material_kinds = 0;
     for (uint64_t i = 0; i < s->n_materials; ++i) ctx->material_kinds |= 1u << s->materials[i].kind;
     return MRT_OK;
@@ -1341,7 +1351,7 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
-    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths, 0u, {}};
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), kRefillLanes, ctx->opt_finish_paths, 0u, {}};
     const unsigned aov_grid = (unsigned)((npix + 127) / 128);
     if (ctx->scene.has_alpha) k_aov<true, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     else if (ctx->scene.n_volumes) k_aov<false, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
@@ -1420,7 +1430,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     st.render_ms = st.extend_ms = st.shade_ms = st.generate_ms = 0.0f;
     st.scene_bytes = ctx->scene_bytes;
     if (total == 0) { st.pool_slots = ctx->pool.capacity; return MRT_OK; }
-    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes, ctx->opt_finish_paths, 0u, {}};
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes ? ctx->opt_refill_lanes : ctx->auto_refill_lanes, ctx->opt_finish_paths, 0u, {}};
     const uint32_t regions = shade_regions(ctx, rp.region);
     if ((rc = ensure_pool(ctx, total, regions))) return rc;
     st.pool_slots = ctx->pool.capacity;
@@ -1575,7 +1585,7 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             ctx->opt_pool_slots = value / 1024 * 1024;
             return MRT_OK;
         case MRT_OPT_REFILL_LANES:
-            if (value < 1 || value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [1, 32]");
+            if (value > 32) return fail(ctx, MRT_E_INVALID, "lane threshold out of range [0, 32]");
             ctx->opt_refill_lanes = (uint32_t)value;
             return MRT_OK;
         case MRT_OPT_FINISH_PATHS:

@@ -4,13 +4,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mass_raytrace_b200 import NativeScene, Renderer, scenes
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["cornell", "book1", "book2", "mesh1m"]
-combos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]] or [(4, 100, 32), (4, 100, 30), (4, 100, 28), (4, 100, 24)]
+combos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]] or [(4, 100, 32), (4, 100, 28), (4, 100, 24), (4, 100, 20), (4, 100, 16), (4, 100, 12), (4, 100, 8)]
 tmp = tempfile.mkdtemp()
 def build(name):
     if name == "cornell": return scenes.cornell_box(1.0), 1024, 1024, 16
     if name == "book1": return scenes.book1_spheres(1.5, 0.1), 1200, 800, 10
     if name == "book2": return scenes.book2_final(), 1920, 1080, 8
     if name == "menger": return scenes.menger(levels=4), 1920, 1080, 8
+    if name == "mesh10m":
+        paths, mds = [], []
+        for i in range(10):
+            q = os.path.join(tmp, f"m{i}.ply"); n, md = scenes.write_synthetic_ply(q, 1024, 512, seed=100 + i); paths.append(q); mds.append(md)
+        return scenes.multi_mesh(paths, mds), 3840, 2160, 2
     if name == "mesh1m":
         n, md = scenes.write_synthetic_ply(os.path.join(tmp, "m.ply"), 1024, 512, seed=1)
         return scenes.lucy_layout(os.path.join(tmp, "m.ply"), md, grid=0), 1920, 1080, 8
