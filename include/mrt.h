@@ -262,10 +262,12 @@ enum {
     MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
     MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^24 (0 = default 2^22) */
     MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes of continuing rays once this many of a warp's 32 lanes are idle;
-                                 0 (default) = by scene: 32 (whole batches), or 20 when a mesh's tree is deep */
+                                 0 (default) = by scene: 32 (whole batches), or 12 when a mesh's tree is deep */
     MRT_OPT_DEVICE_BUILD = 11, /* mrt_scene_upload builds the BLAS of meshes of >= 16384 triangles ON THE GPU (linear BVH, ~3 ms per million
                                   triangles; default 1). 0: the host's SAH builder for every mesh (0.25 s per million triangles, ~13 % faster
                                   traversal): worth it for renders of thousands of samples per pixel */
+    MRT_OPT_NODE_BURST = 12,   /* k_extend: at most this many node visits per lane before the warp tests its pending leaves; 0 (default) = by scene:
+                                  no bound, or 4 when a mesh's tree is deep */
     MRT_OPT_BVH_LEAF_TRIS = 9, /* SAH rebuild at the next mrt_scene_upload: most triangles per BLAS leaf, 1..4 (default 4) */
     MRT_OPT_BVH_TRI_COST = 10, /* SAH rebuild: cost of one triangle test in hundredths of a node visit (default 100) */
     MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 65536, 0 = off) */

@@ -57,6 +57,7 @@ struct RenderParams {
     uint32_t w, h, npix, spp_begin, max_depth;
     uint2 seed;
     uint32_t refill_lanes;   // k_extend commits and refills finished lanes once this many lanes of a warp are idle
+    uint32_t node_burst;     // k_extend: node visits per lane between two looks at the leaves
     uint32_t finish_paths;   // drain threshold of k_finish (0 = never)
     uint32_t capacity;       // rays in flight (entries per queue)
     uint8_t region[Q_COUNT + 3];  // shade-queue region of each queue kind (only the material kinds the scene uses get one)
@@ -175,11 +176,14 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamer
 // (all at the root, then all a few nodes from their next leaf); refilling lanes early -- even for the price of a few
 // shared-memory loads from a prefetched ring -- mixes rays that need five node visits with rays that need one and costs more
 // warp instructions than the idle lanes save. Under a deep BLAS (a mesh of tens of thousands of triangles or more) ray lengths
-// vary so much that the idle tail dominates (5-7 of 32 lanes active on bounce rays): there continuing rays are refilled at 20
-// idle lanes (-7 % k_extend time on the 1 M- and 10 M-triangle scenes); camera rays always run as whole batches.
+// vary so much that the idle tail dominates (5-7 of 32 lanes active on bounce rays): there continuing rays are refilled at 12
+// idle lanes, and a lane makes at most 4 node visits before the warp looks at its pending leaves again, so that a freshly
+// started ray (20 levels from its first leaf) does not hold up the lanes that are one or two visits from theirs
+// (-13 % / -17 % k_extend time on the 1 M- / 10 M-triangle scenes); camera rays always run as whole batches.
 // Leaving an instance is free: stack entries pushed before the instance was entered lie below inst_base, and popping one
 // restores the world-space ray from shared memory (no sentinel entries).
-constexpr uint32_t kRefillLanes = 32, kRefillLanesDeep = 20;  // defaults (shallow / deep BLAS); MRT_OPT_REFILL_LANES overrides them
+constexpr uint32_t kRefillLanes = 32, kRefillLanesDeep = 12;  // defaults (shallow / deep BLAS); MRT_OPT_REFILL_LANES overrides them
+constexpr uint32_t kNodeBurst = 0xFFFFFFFFu, kNodeBurstDeep = 4;  // node visits per lane between two looks at the leaves; MRT_OPT_NODE_BURST
 constexpr int kDeepBlas = 12;                                 // inner-node levels from which a BLAS counts as deep
 constexpr int kExtendThreads = 128;
 
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
     // always runs a batch of them to the end (32); continuing rays use rp.refill_lanes
     const uint32_t n_cont = q->n_cont;
     uint32_t refill_lanes = rp.refill_lanes;
+    const uint32_t node_burst = rp.node_burst;
     VisitCounters cnt{0, 0, 0, 0, 0};
     uint32_t stack[kStackSize];
     Traversal T;
@@ -273,8 +278,13 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
             pending = true;
         }
         if (active) {
-            while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
-            if (T.ref != kNone) trav_leaf<COUNT, ALPHA, VOLUME>(sc, T, stack, ws, 0.001f, key, &cnt);
+            // at most node_burst node visits before the warp looks at its leaves again (0xFFFFFFFF: descend all the way to the next leaf)
+            if (node_burst == kNodeBurst) {  // (warp-uniform) the unbounded loop carries no counter
+                while (ref_is_node(T.ref)) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
+            } else {
+                for (uint32_t k = 0; k < node_burst && ref_is_node(T.ref); ++k) trav_node<COUNT>(sc, T, stack, 0.001f, &cnt);
+            }
+            if (T.ref != kNone && !ref_is_node(T.ref)) trav_leaf<COUNT, ALPHA, VOLUME>(sc, T, stack, ws, 0.001f, key, &cnt);
         }
     }
     if (COUNT) {
@@ -585,7 +595,8 @@ struct mrt_context {
     int* d_depths = nullptr;        // tree depth of each GPU-built BLAS
     int* h_depths = nullptr;        // pinned
     uint32_t opt_refill_lanes = 0;  // 0 = by scene: kRefillLanesDeep under a deep BLAS, else kRefillLanes
-    uint32_t auto_refill_lanes = kRefillLanes;
+    uint32_t auto_refill_lanes = kRefillLanes, auto_node_burst = kNodeBurst;
+    uint32_t opt_node_burst = 0;  // 0 = by scene
     mrt_stats stats{};
     int grid_extend[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [count visits][0 plain, 1 volumes, 2 alpha-tested triangles (+ volumes)]
     int grid_shade = 0, grid_generate = 0;
@@ -1308,6 +1319,7 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     ctx->scene = d;
     ctx->has_scene = true;
     ctx->auto_refill_lanes = max_blas_depth >= kDeepBlas ? kRefillLanesDeep : kRefillLanes;
+    ctx->auto_node_burst = max_blas_depth >= kDeepBlas ? kNodeBurstDeep : kNodeBurst;
     ctx->material_kinds = 0;
     for (uint64_t i = 0; i < s->n_materials; ++i) ctx->material_kinds |= 1u << s->materials[i].kind;
     return MRT_OK;
@@ -1351,7 +1363,7 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
     if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
     if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
-    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), kRefillLanes, ctx->opt_finish_paths, 0u, {}};
+    RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), kRefillLanes, kNodeBurst, ctx->opt_finish_paths, 0u, {}};
     const unsigned aov_grid = (unsigned)((npix + 127) / 128);
     if (ctx->scene.has_alpha) k_aov<true, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
     else if (ctx->scene.n_volumes) k_aov<false, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
@@ -1430,7 +1442,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     st.render_ms = st.extend_ms = st.shade_ms = st.generate_ms = 0.0f;
     st.scene_bytes = ctx->scene_bytes;
     if (total == 0) { st.pool_slots = ctx->pool.capacity; return MRT_OK; }
-    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes ? ctx->opt_refill_lanes : ctx->auto_refill_lanes, ctx->opt_finish_paths, 0u, {}};
+    RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes ? ctx->opt_refill_lanes : ctx->auto_refill_lanes, ctx->opt_node_burst ? ctx->opt_node_burst : ctx->auto_node_burst, ctx->opt_finish_paths, 0u, {}};
     const uint32_t regions = shade_regions(ctx, rp.region);
     if ((rc = ensure_pool(ctx, total, regions))) return rc;
     st.pool_slots = ctx->pool.capacity;
@@ -1593,6 +1605,7 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             ctx->opt_finish_paths = (uint32_t)value;
             return MRT_OK;
         case MRT_OPT_DEVICE_BUILD: ctx->opt_device_build = value != 0; return MRT_OK;
+        case MRT_OPT_NODE_BURST: ctx->opt_node_burst = (uint32_t)value; return MRT_OK;
         case MRT_OPT_BVH_LEAF_TRIS:
             if (value < 1 || value > 4) return fail(ctx, MRT_E_INVALID, "leaf size out of range [1, 4]");
             ctx->opt_leaf_tris = (uint32_t)value;

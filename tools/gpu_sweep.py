@@ -24,8 +24,9 @@ for name in names:
     (w, c), W, H, spp = build(name)
     host = NativeScene(w, c)
     r = Renderer(0)
-    for leaf, cost, refill in combos:
-        r.set_option(Renderer.OPT_BVH_LEAF_TRIS, leaf); r.set_option(Renderer.OPT_BVH_TRI_COST, cost); r.set_option(Renderer.OPT_REFILL_LANES, refill)
+    for combo in combos:
+        leaf, cost, refill = combo[:3]; burst = combo[3] if len(combo) > 3 else 0
+        r.set_option(Renderer.OPT_BVH_LEAF_TRIS, leaf); r.set_option(Renderer.OPT_BVH_TRI_COST, cost); r.set_option(Renderer.OPT_REFILL_LANES, refill); r.set_option(Renderer.OPT_NODE_BURST, burst)
         r.set_scene(host)
         r.set_option(Renderer.OPT_TIME_KERNELS, 0)
         r.reset(W, H); r.accumulate(0, 2)
@@ -38,6 +39,6 @@ for name in names:
         r.set_option(Renderer.OPT_TIME_KERNELS, 0); r.set_option(Renderer.OPT_COUNT_VISITS, 1)
         r.reset(W, H); r.accumulate(0, 1); cs = r.stats()
         r.set_option(Renderer.OPT_COUNT_VISITS, 0)
-        print(f"{name:8s} leaf {leaf} cost {cost:3d} refill {refill:2d}: render {plain:8.2f} ms = {st['rays']/plain/1e3:7.1f} Mrays/s | extend {st['extend_ms']:7.2f} shade {st['shade_ms']:6.2f} gen {st['generate_ms']:5.2f} | "
+        print(f"{name:8s} leaf {leaf} cost {cost:3d} refill {refill:2d} burst {burst:2d}: render {plain:8.2f} ms = {st['rays']/plain/1e3:7.1f} Mrays/s | extend {st['extend_ms']:7.2f} shade {st['shade_ms']:6.2f} gen {st['generate_ms']:5.2f} | "
               f"nodes/ray {cs['node_visits']/cs['rays']:5.2f} tris/ray {cs['tri_tests']/cs['rays']:4.2f} inst/ray {cs['instance_tests']/cs['rays']:4.2f}", flush=True)
     r.close()
