@@ -200,3 +200,33 @@ def test_png_decoder_against_pil(tmp_path):
         open(str(tmp_path / name), "wb").write(data)
         with pytest.raises(RuntimeError, match=msg):
             _texels(NativeScene, str(tmp_path / name))
+
+
+def test_png_decoder_survives_corruption(tmp_path):
+    """Corrupted and truncated PNGs give an error or an image, never a crash or a runaway allocation (the decoder bounds its output by
+    the size the header announces)."""
+    import io
+    import random
+
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (40, 33, 4), dtype=np.uint8)
+    img[:20] = 7
+    buf = io.BytesIO()
+    Image.fromarray(img, "RGBA").save(buf, "PNG")
+    good = buf.getvalue()
+    random.seed(1)
+    decoded = rejected = 0
+    p = str(tmp_path / "fuzz.png")
+    for _ in range(400):
+        b = bytearray(good)
+        for _k in range(random.randint(1, 6)):
+            b[random.randrange(len(b))] = random.randrange(256)
+        if random.random() < 0.2:
+            b = b[:random.randrange(8, len(b))]
+        open(p, "wb").write(b)
+        try:
+            _texels(NativeScene, p)
+            decoded += 1
+        except RuntimeError:
+            rejected += 1
+    assert decoded + rejected == 400 and rejected > 100
