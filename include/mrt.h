@@ -263,9 +263,10 @@ enum {
     MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^24 (0 = default 2^22) */
     MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes of continuing rays once this many of a warp's 32 lanes are idle;
                                  0 (default) = by scene: 32 (whole batches), or 12 when a mesh's tree is deep */
-    MRT_OPT_DEVICE_BUILD = 11, /* mrt_scene_upload builds the BLAS of meshes of >= 16384 triangles ON THE GPU (linear BVH, ~3 ms per million
-                                  triangles; default 1). 0: the host's SAH builder for every mesh (0.25 s per million triangles, ~13 % faster
-                                  traversal): worth it for renders of thousands of samples per pixel */
+    MRT_OPT_DEVICE_BUILD = 11, /* mrt_scene_upload builds trees ON THE GPU (linear BVH, ~3 ms per million primitives): 1 (default) the BLAS of meshes
+                                  of >= 16384 triangles and a TLAS of >= 2^20 objects; 2 also a TLAS of >= 16384 objects; 0 never -- the host's
+                                  SAH builder for everything (0.25 s per million triangles, ~13 % faster traversal of meshes, ~35 % of instance
+                                  lattices): worth it for renders of thousands of samples per pixel */
     MRT_OPT_NODE_BURST = 12,   /* k_extend: at most this many node visits per lane before the warp tests its pending leaves; 0 (default) = by scene:
                                   no bound, or 4 when a mesh's tree is deep */
     MRT_OPT_BVH_LEAF_TRIS = 9, /* SAH rebuild at the next mrt_scene_upload: most triangles per BLAS leaf, 1..4 (default 4) */

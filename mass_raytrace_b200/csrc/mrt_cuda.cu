@@ -590,7 +590,8 @@ struct mrt_context {
     uint64_t opt_pool_slots = 0;
     uint32_t opt_finish_paths = 65536;
     uint32_t opt_leaf_tris = 4, opt_tri_cost = 100;
-    bool opt_device_build = true;   // MRT_OPT_DEVICE_BUILD: big meshes get an LBVH built on the GPU instead of the host's SAH tree
+    uint32_t opt_device_build = 1;  // MRT_OPT_DEVICE_BUILD: 0 host SAH everywhere; 1 GPU LBVH for big meshes (and for a TLAS of >= 2^20 objects);
+                                    // 2 also for a TLAS of >= 16384 objects
     DevBuf build_scratch;           // raw vertices + work arrays of the GPU builder (grow-only)
     int* d_depths = nullptr;        // tree depth of each GPU-built BLAS
     int* h_depths = nullptr;        // pinned
@@ -891,12 +892,14 @@ static int subtree_depth(const mrt_scene_desc* s, uint32_t root, bool tlas, std:
 
 constexpr int kRetryOnHost = 1;  // internal: the GPU-built tree is too deep for the traversal stack
 constexpr uint32_t kDeviceBuildMin = 16384, kDeviceBuildMaxMeshes = 1024;
+constexpr size_t kDeviceTlasMin = 1u << 20;  // an LBVH over instances traverses markedly worse than the SAH tree (Menger sponge: +37 % k_extend), so
+                                             // the TLAS goes to the GPU only where the host build would take seconds
 
 static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device);
 
 int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if (!ctx) return MRT_E_INVALID;
-    int rc = scene_upload_impl(ctx, s, ctx->opt_device_build);
+    int rc = scene_upload_impl(ctx, s, ctx->opt_device_build != 0);
     if (rc == kRetryOnHost) rc = scene_upload_impl(ctx, s, false);
     return rc;
 }
@@ -1017,6 +1020,8 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     int max_tlas_depth = tlas_depth, max_blas_depth = blas_depth;
     uint32_t device_root = kNone;  // stays kNone for an empty world
     std::vector<uint32_t> device_meshes;  // BLAS indices the GPU builds
+    bool tlas_on_device = false;          // the world has so many objects that the GPU builds the TLAS too
+    std::vector<mrt_build::Prim> tlas_prims;
     if (keep) {
         nodes.resize(s->n_nodes);
         for (uint64_t i = 0; i < s->n_nodes; ++i) {
@@ -1153,7 +1158,10 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
                 }
             }
         }
-        if (!prims.empty()) {
+        if (allow_device && prims.size() >= (ctx->opt_device_build >= 2 ? (size_t)kDeviceBuildMin : kDeviceTlasMin)) {
+            tlas_on_device = true;  // built on the GPU after the upload, from these boxes (its root is set below)
+            tlas_prims.swap(prims);
+        } else if (!prims.empty()) {
             mrt_build::Tree t = mrt_build::build_sah(prims, 1, 28, 4.0f);
             max_tlas_depth = std::max(t.depth, 1);
             const mrt_build::Prim* pp = prims.data();
@@ -1168,6 +1176,12 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
         device_node_base[k] = (uint32_t)n_nodes_total;
         blas_root[device_meshes[k]] = MRT_REF(MRT_PRIM_NODE, (uint32_t)n_nodes_total);
         n_nodes_total += s->blas[device_meshes[k]].n_tris - 1;
+    }
+    uint32_t tlas_node_base = 0;
+    if (tlas_on_device) {
+        tlas_node_base = (uint32_t)n_nodes_total;
+        device_root = MRT_REF(MRT_PRIM_NODE, tlas_node_base);
+        n_nodes_total += tlas_prims.size() - 1;
     }
     if (n_nodes_total >= (1ull << 29)) return fail(ctx, MRT_E_INVALID, "too many BVH nodes for 29-bit references");
     lap("build");
@@ -1284,14 +1298,39 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     d.has_alpha = any_alpha;
     d.bg = s->background;
     lap("copy");
+    if (tlas_on_device) {  // ---- the TLAS of a world with many objects: boxes + references up, tree built on the GPU ---------
+        const size_t n = tlas_prims.size(), cubb = lbvh::cub_temp_bytes(n);
+        if (!ctx->d_depths) {
+            MRT_CUDA(cudaMalloc(&ctx->d_depths, (kDeviceBuildMaxMeshes + 1) * sizeof(int)));
+            MRT_CUDA(cudaMallocHost(&ctx->h_depths, (kDeviceBuildMaxMeshes + 1) * sizeof(int)));
+        }
+        const size_t refs_bytes = (n * 4 + 255) / 256 * 256;
+        if ((rc = grow(ctx, ctx->build_scratch, refs_bytes + lbvh::scratch_bytes(n, cubb)))) return rc;
+        std::vector<float4> lo(n), hi(n);
+        std::vector<uint32_t> refs(n);
+        for (size_t i = 0; i < n; ++i) {
+            lo[i] = make_float4(tlas_prims[i].lo[0], tlas_prims[i].lo[1], tlas_prims[i].lo[2], 0.0f);
+            hi[i] = make_float4(tlas_prims[i].hi[0], tlas_prims[i].hi[1], tlas_prims[i].hi[2], 0.0f);
+            refs[i] = tlas_prims[i].ref;
+        }
+        uint32_t* d_refs = static_cast<uint32_t*>(ctx->build_scratch.p);
+        lbvh::Scratch sc = lbvh::carve(static_cast<char*>(ctx->build_scratch.p) + refs_bytes, n, cubb);
+        if ((rc = stage_copy(ctx, d_refs, refs.data(), n * 4))) return rc;
+        if ((rc = stage_copy(ctx, sc.box_lo, lo.data(), n * 16))) return rc;
+        if ((rc = stage_copy(ctx, sc.box_hi, hi.data(), n * 16))) return rc;
+        MRT_CUDA(lbvh::build_objects(ctx->stream, sc, (uint32_t)n, d_refs, d_nodes, tlas_node_base, ctx->d_depths + kDeviceBuildMaxMeshes));
+        MRT_CUDA(cudaMemcpyAsync(ctx->h_depths + kDeviceBuildMaxMeshes, ctx->d_depths + kDeviceBuildMaxMeshes, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the scratch is reused by the mesh builds below; lo / hi / refs go out of scope
+        max_tlas_depth = std::max(ctx->h_depths[kDeviceBuildMaxMeshes], 1);
+    }
     if (!device_meshes.empty()) {  // ---- build the big meshes on the GPU, one after the other on the upload stream --------
         const uint8_t* d_mat_alpha = nullptr;
         std::vector<uint8_t> ma(s->n_materials);
         for (uint64_t i = 0; i < s->n_materials; ++i) ma[i] = mat_alpha[i] > 0 ? 1 : 0;
         if ((rc = upload(ctx, ma.data(), ma.size(), &d_mat_alpha))) return rc;
         if (!ctx->d_depths) {
-            MRT_CUDA(cudaMalloc(&ctx->d_depths, kDeviceBuildMaxMeshes * sizeof(int)));
-            MRT_CUDA(cudaMallocHost(&ctx->h_depths, kDeviceBuildMaxMeshes * sizeof(int)));
+            MRT_CUDA(cudaMalloc(&ctx->d_depths, (kDeviceBuildMaxMeshes + 1) * sizeof(int)));
+            MRT_CUDA(cudaMallocHost(&ctx->h_depths, (kDeviceBuildMaxMeshes + 1) * sizeof(int)));
         }
         size_t need = 0;
         for (uint32_t bi : device_meshes) {
@@ -1311,7 +1350,7 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
         MRT_CUDA(cudaMemcpyAsync(ctx->h_depths, ctx->d_depths, device_meshes.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     MRT_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
-    if (!device_meshes.empty()) {
+    if (!device_meshes.empty() || tlas_on_device) {
         for (size_t k = 0; k < device_meshes.size(); ++k) max_blas_depth = std::max(max_blas_depth, ctx->h_depths[k]);
         lap("gpu build");
         if (max_tlas_depth + max_blas_depth + 2 > kStackSize) return kRetryOnHost;  // pathological Morton order: let the host's SAH builder do it
@@ -1604,7 +1643,10 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
             if (value > (1u << 22)) return fail(ctx, MRT_E_INVALID, "finish threshold out of range [0, 2^22]");
             ctx->opt_finish_paths = (uint32_t)value;
             return MRT_OK;
-        case MRT_OPT_DEVICE_BUILD: ctx->opt_device_build = value != 0; return MRT_OK;
+        case MRT_OPT_DEVICE_BUILD:
+            if (value > 2) return fail(ctx, MRT_E_INVALID, "device build mode out of range [0, 2]");
+            ctx->opt_device_build = (uint32_t)value;
+            return MRT_OK;
         case MRT_OPT_NODE_BURST: ctx->opt_node_burst = (uint32_t)value; return MRT_OK;
         case MRT_OPT_BVH_LEAF_TRIS:
             if (value < 1 || value > 4) return fail(ctx, MRT_E_INVALID, "leaf size out of range [1, 4]");

@@ -1,4 +1,5 @@
-// mrt_lbvh.cuh — BLAS construction ON THE GPU (option MRT_OPT_DEVICE_BUILD): linear BVH over 63-bit Morton codes.
+// mrt_lbvh.cuh — BVH construction ON THE GPU (option MRT_OPT_DEVICE_BUILD): linear BVH over 63-bit Morton codes, for the BLAS of a
+// big mesh (from its raw triangles) and for the TLAS of a world with many objects (from their boxes).
 //
 // The reference rebuilds every tree on one CPU thread whenever a frame's world is generated (BvhNode::new geom.rs:109-161,
 // called from Model::new :281-292 and World::build_bvh world.rs:117-122, per frame at main.rs:107-112). A closest hit does not
@@ -71,6 +72,33 @@ __global__ void k_lbvh_boxes(const float* __restrict__ raw, uint32_t n, float4* 
         }
         box_lo[i] = make_float4(blo[0], blo[1], blo[2], 0.0f);
         box_hi[i] = make_float4(bhi[0], bhi[1], bhi[2], 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_down_sync(0xffffffffu, lo[k], off));
+            hi[k] = fmaxf(hi[k], __shfl_down_sync(0xffffffffu, hi[k], off));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (lo[k] < inf) atomicMin(&cbounds[k], float_to_ordered(lo[k]));
+            if (hi[k] > -inf) atomicMax(&cbounds[3 + k], float_to_ordered(hi[k]));
+        }
+    }
+}
+
+// centroid bounds of boxes that are already on the device (TLAS: the objects' world boxes)
+__global__ void k_lbvh_box_bounds(const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, uint32_t n, int* cbounds) {
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = box_lo[i], b = box_hi[i];
+        const float c[3] = {0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float ck = isfinite(c[k]) ? c[k] : 0.0f;
+            lo[k] = fminf(lo[k], ck);
+            hi[k] = fmaxf(hi[k], ck);
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -188,17 +216,17 @@ __global__ void k_lbvh_refit(int n, const int2* __restrict__ child, const int* _
     }
 }
 
-__global__ void k_lbvh_live(int m, const uint2* __restrict__ range, uint32_t* live) {
+__global__ void k_lbvh_live(int m, const uint2* __restrict__ range, uint32_t* live, uint32_t max_leaf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint2 r = range[i];
-    live[i] = (i == 0 || r.y - r.x + 1u > kMaxLeaf) ? 1u : 0u;
+    live[i] = (i == 0 || r.y - r.x + 1u > max_leaf) ? 1u : 0u;
 }
 
 __global__ void k_lbvh_emit(int m, const int2* __restrict__ child, const uint2* __restrict__ range, const uint32_t* __restrict__ live,
                             const uint32_t* __restrict__ new_index, const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ box_lo,
                             const float4* __restrict__ box_hi, const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, DNode* nodes,
-                            uint32_t node_base, uint32_t tri_base) {
+                            uint32_t node_base, uint32_t tri_base, const uint32_t* __restrict__ obj_refs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m || !live[i]) return;
     const int2 c = child[i];
@@ -211,7 +239,7 @@ __global__ void k_lbvh_emit(int m, const int2* __restrict__ child, const uint2* 
             const uint32_t pos = (uint32_t)~ch[k], t = idx_sorted[pos];
             lo[k] = box_lo[t];
             hi[k] = box_hi[t];
-            ref[k] = MRT_REF(MRT_PRIM_TRIANGLE, tri_base + pos);
+            ref[k] = obj_refs ? obj_refs[t] : MRT_REF(MRT_PRIM_TRIANGLE, tri_base + pos);  // TLAS: the object's own reference
         } else {
             lo[k] = node_lo[ch[k]];
             hi[k] = node_hi[ch[k]];
@@ -281,30 +309,52 @@ inline Scratch carve(void* base, size_t n, size_t cub_bytes) {
     return s;
 }
 
-// Builds the BLAS of one mesh on `stream`. raw: n * 9 floats on the device (caller order). Nodes go to nodes[node_base ...] (at
-// most n - 1 of them, root first), triangles to tri_verts / tri_map [first_tri, first_tri + n). depth_out (device) receives the
-// tree depth in inner nodes.
-inline cudaError_t build(cudaStream_t stream, const Scratch& s, const float* raw, uint32_t n, const mrt_tri_shading* shading, const uint8_t* mat_alpha,
-                         uint32_t first_tri, DNode* nodes, uint32_t node_base, DTriVerts* tri_verts, uint32_t* tri_map, int* depth_out) {
+// sort, tree, refit, numbering and node emission over boxes + Morton keys that are already in the scratch arrays
+inline cudaError_t finish(cudaStream_t stream, const Scratch& s, uint32_t n, uint32_t max_leaf, DNode* nodes, uint32_t node_base, uint32_t tri_base,
+                          const uint32_t* obj_refs, int* depth_out) {
     const int m = (int)n - 1;
     const int T = 256;
     const unsigned gn = (unsigned)((n + T - 1) / T), gm = (unsigned)((m + T - 1) / T);
-    k_lbvh_init<<<1, 32, 0, stream>>>(s.cbounds);
-    k_lbvh_boxes<<<std::min(gn, 148u * 8u), T, 0, stream>>>(raw, n, s.box_lo, s.box_hi, s.cbounds);
-    k_lbvh_morton<<<std::min(gn, 148u * 8u), T, 0, stream>>>(s.box_lo, s.box_hi, n, s.cbounds, s.keys, s.idx);
     size_t tb = s.cub_temp_bytes;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(s.cub_temp, tb, s.keys, s.keys_sorted, s.idx, s.idx_sorted, (int)n, 0, 63, stream);
     if (e != cudaSuccess) return e;
     k_lbvh_tree<<<gm, T, 0, stream>>>(s.keys_sorted, (int)n, s.child, s.range, s.parent, s.leaf_parent);
     if ((e = cudaMemsetAsync(s.visits, 0, (size_t)m * 4, stream)) != cudaSuccess) return e;
     k_lbvh_refit<<<gn, T, 0, stream>>>((int)n, s.child, s.parent, s.leaf_parent, s.idx_sorted, s.box_lo, s.box_hi, s.node_lo, s.node_hi, s.depth, s.visits);
-    k_lbvh_live<<<gm, T, 0, stream>>>(m, s.range, s.live);
+    k_lbvh_live<<<gm, T, 0, stream>>>(m, s.range, s.live, max_leaf);
     tb = s.cub_temp_bytes;
     if ((e = cub::DeviceScan::ExclusiveSum(s.cub_temp, tb, s.live, s.new_index, m, stream)) != cudaSuccess) return e;
-    k_lbvh_emit<<<gm, T, 0, stream>>>(m, s.child, s.range, s.live, s.new_index, s.idx_sorted, s.box_lo, s.box_hi, s.node_lo, s.node_hi, nodes, node_base, first_tri);
-    k_lbvh_gather<<<std::min(gn, 148u * 8u), T, 0, stream>>>(n, raw, s.idx_sorted, shading, mat_alpha, first_tri, tri_verts, tri_map);
+    k_lbvh_emit<<<gm, T, 0, stream>>>(m, s.child, s.range, s.live, s.new_index, s.idx_sorted, s.box_lo, s.box_hi, s.node_lo, s.node_hi, nodes, node_base, tri_base,
+                                     obj_refs);
     if ((e = cudaMemcpyAsync(depth_out, s.depth, sizeof(int), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
     return cudaGetLastError();
+}
+
+// Builds the BLAS of one mesh on `stream`. raw: n * 9 floats on the device (caller order). Nodes go to nodes[node_base ...] (at
+// most n - 1 of them, root first), triangles to tri_verts / tri_map [first_tri, first_tri + n). depth_out (device) receives the
+// tree depth in inner nodes.
+inline cudaError_t build(cudaStream_t stream, const Scratch& s, const float* raw, uint32_t n, const mrt_tri_shading* shading, const uint8_t* mat_alpha,
+                         uint32_t first_tri, DNode* nodes, uint32_t node_base, DTriVerts* tri_verts, uint32_t* tri_map, int* depth_out) {
+    const int T = 256;
+    const unsigned gn = std::min((unsigned)((n + T - 1) / T), 148u * 8u);
+    k_lbvh_init<<<1, 32, 0, stream>>>(s.cbounds);
+    k_lbvh_boxes<<<gn, T, 0, stream>>>(raw, n, s.box_lo, s.box_hi, s.cbounds);
+    k_lbvh_morton<<<gn, T, 0, stream>>>(s.box_lo, s.box_hi, n, s.cbounds, s.keys, s.idx);
+    cudaError_t e = finish(stream, s, n, kMaxLeaf, nodes, node_base, first_tri, nullptr, depth_out);
+    if (e != cudaSuccess) return e;
+    k_lbvh_gather<<<gn, T, 0, stream>>>(n, raw, s.idx_sorted, shading, mat_alpha, first_tri, tri_verts, tri_map);
+    return cudaGetLastError();
+}
+
+// Builds the TLAS over n objects whose world boxes are already in s.box_lo / s.box_hi; obj_refs[i] is object i's reference
+// (sphere, instance, volume). One object per leaf. Nodes go to nodes[node_base ...], root first.
+inline cudaError_t build_objects(cudaStream_t stream, const Scratch& s, uint32_t n, const uint32_t* obj_refs, DNode* nodes, uint32_t node_base, int* depth_out) {
+    const int T = 256;
+    const unsigned gn = std::min((unsigned)((n + T - 1) / T), 148u * 8u);
+    k_lbvh_init<<<1, 32, 0, stream>>>(s.cbounds);
+    k_lbvh_box_bounds<<<gn, T, 0, stream>>>(s.box_lo, s.box_hi, n, s.cbounds);
+    k_lbvh_morton<<<gn, T, 0, stream>>>(s.box_lo, s.box_hi, n, s.cbounds, s.keys, s.idx);
+    return finish(stream, s, n, 1u, nodes, node_base, 0u, obj_refs, depth_out);
 }
 
 }  // namespace lbvh

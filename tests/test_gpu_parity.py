@@ -158,6 +158,35 @@ def test_aov_menger_sponge_instances(renderer):
     stat_compare(renderer, world, camera, 96, 54, 32)
 
 
+def test_aov_tlas_built_on_the_gpu(renderer):
+    """MRT_OPT_DEVICE_BUILD = 2: a world of >= 16384 objects gets its TLAS built on the GPU too (mrt_lbvh.cuh, one object per leaf;
+    by default only from 2^20 objects): 20,000 spheres and the instances of a cube, primary rays against the oracle; then the same
+    world through the host's SAH builder."""
+    rs = np.random.RandomState(4)
+    world = World(SkyBackground())
+    mats = [Lambertian(SolidColor((0.8, 0.3, 0.3, 1))), Metal(0.1, SolidColor((0.8, 0.8, 0.8, 1))), Dielectric(1.5)]
+    c = rs.uniform(-30, 30, (20000, 3)).astype(np.float32)
+    for i in range(20000):
+        world.add(Sphere(mats[i % 3], V3(c[i, 0], abs(c[i, 1]) * 0.3 + 0.3, c[i, 2]), 0.3))
+    from mass_raytrace_b200 import PlyLoader
+    cube = Model(PlyLoader.load(scenes.CUBE_PLY))
+    for i in range(200):
+        world.add(cube.instance(V3(*rs.uniform(-25, 25, 3)), V3(*rs.uniform(0, 1, 3)), V3(0.5, 0.5, 0.5)).with_material(mats[0]))
+    world.add(Sphere(mats[0], V3(0, -1000, 0), 1000.0))
+    world.build_bvh()
+    camera = Camera(40.0, V3(0, 12, 45), V3(0, 2, 0), V3(0, 1, 0), 16.0 / 9.0, 0.0, 45.0)
+    o = OracleScene(world, camera).render_aov(480, 270)
+    try:
+        for device_build in (2, 0):
+            renderer.set_option(renderer.OPT_DEVICE_BUILD, device_build)
+            renderer.set_scene(NativeScene(world, camera))
+            g = renderer.render_aov(480, 270)
+            check_aov(g, o, albedo_exact=False)
+            assert len(np.unique(g["object"])) > 2000
+    finally:
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)
+
+
 def test_aov_world_without_bvh(renderer):
     # World::intersect before build_bvh: linear closest hit over the object list (world.rs:131-144); > 8 roots uses the list path
     for n_spheres in (5, 14):
