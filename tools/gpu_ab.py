@@ -11,6 +11,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         if base == "cornell": (w, c), W, H, spp = scenes.cornell_box(1.0), 1024, 1024, 16
         elif base == "menger": (w, c), W, H, spp = scenes.menger(levels=4), 1920, 1080, 8
         elif base == "book2": (w, c), W, H, spp = scenes.book2_final(), 1920, 1080, 8
+        elif base == "mesh10m":
+            tmp = tempfile.mkdtemp(); paths, mds = [], []
+            for i in range(10):
+                q = os.path.join(tmp, f"m{i}.ply"); n, md = scenes.write_synthetic_ply(q, 1024, 512, seed=100 + i); paths.append(q); mds.append(md)
+            (w, c), W, H, spp = scenes.multi_mesh(paths, mds), 3840, 2160, 2
         elif base == "mesh1m":
             tmp = tempfile.mkdtemp(); n, md = scenes.write_synthetic_ply(os.path.join(tmp, "m.ply"), 1024, 512, seed=1)
             (w, c), W, H, spp = scenes.lucy_layout(os.path.join(tmp, "m.ply"), md, grid=0), 1920, 1080, 8
