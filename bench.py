@@ -373,7 +373,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "spp_per_gpu_per_step": spp, "max_depth": 50,
                        "partition": f"samples per pixel split over {world_size} rank(s), one NCCL int64 sum-reduce per step" if world_size > 1 else "single GPU",
-                       "l2": "flushed between steps (256 MiB write); the ray / shade queues of one iteration (>= 460 MB at 4M paths in flight) also exceed the 126 MB L2",
+                       "l2": "flushed between steps (256 MiB write); the ray / shade queues of one iteration (1.8 GB at 16M paths in flight) also exceed the 126 MB L2",
                        "scene_build_s": build_s, "rays_per_path": rays / paths,
                        "bvh": "host SAH for every mesh" if args.bvh == "sah" else "GPU LBVH for meshes of >= 16384 triangles, host SAH otherwise"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

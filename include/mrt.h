@@ -260,7 +260,7 @@ int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8
 enum {
     MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */
     MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
-    MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^24 (0 = default 2^22) */
+    MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^26 (0 = default 2^24; 96 B + 64 B per material kind in the scene each) */
     MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes of continuing rays once this many of a warp's 32 lanes are idle;
                                  0 (default) = by scene: 32 (whole batches), or 12 when a mesh's tree is deep */
     MRT_OPT_DEVICE_BUILD = 11, /* mrt_scene_upload builds trees ON THE GPU (linear BVH, ~3 ms per million primitives): 1 (default) the BLAS of meshes
