@@ -304,11 +304,12 @@ def main():
              B_INSTANCE * per_ray["instance_tests"] + B_QUEUE_EXTEND)
     peak, peak_src = measured_peak()
     achieved = (b_ray * rays_local / max(ext_launches, 1)) / (ext_ms / max(ext_launches, 1) * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-    traffic = None
+    traffic = None  # DRAM bytes per launch: the per-ray figure of an ncu capture (profiles/extend_dram_bytes.json) x this run's rays per launch
     tpath = os.path.join(ROOT, "profiles", "extend_dram_bytes.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            per_ray_dram = json.load(open(tpath)).get(args.workload)
+            traffic = per_ray_dram * rays_local / max(ext_launches, 1) if per_ray_dram else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
