@@ -71,7 +71,7 @@ typedef struct mrt_tri_shading {
 
 /* the Arc<BvhNode> a Model owns  geom.rs:275-278 */
 typedef struct mrt_blas {
-    uint32_t root;      /* prim ref of the BLAS root (a NODE) */
+    uint32_t root;      /* prim ref of the BLAS root (a NODE); MRT_REF_NONE = no caller tree (not with MRT_SCENE_KEEP_TOPOLOGY) */
     uint32_t first_tri; /* triangles of this mesh are [first_tri, first_tri + n_tris) */
     uint32_t n_tris;
     uint32_t n_nodes;

@@ -23,6 +23,11 @@ void mrth_scene_free(mrth_scene*);
 const char* mrth_last_error(mrth_scene*);
 void mrth_seed(mrth_scene*, uint64_t seed); /* fastrand::seed main.rs:86 — drives BVH split axes (geom.rs:111) */
 float mrth_rand_f32(mrth_scene*);           /* f32::rand() math.rs:244 for scene generation */
+/* on != 0: meshes created from here on carry no reference-topology tree (mrt_blas.root = MRT_REF_NONE, n_nodes = 0) — the
+ * backend builds its own BLAS from the triangle range anyway unless MRT_SCENE_KEEP_TOPOLOGY is set, so the median-split
+ * build of Model::new (geom.rs:281-286) is load time with nothing to show for it. Such a scene cannot be uploaded with
+ * MRT_SCENE_KEEP_TOPOLOGY, and the split-axis draws of the skipped builds are not taken from the scene's generator. */
+void mrth_defer_mesh_bvh(mrth_scene*, int on);
 
 /* texture.rs */
 int mrth_surface_solid(mrth_scene*, float r, float g, float b, float a);

@@ -131,6 +131,7 @@ def scene_api(prefix, with_desc):
         f"{p}_get_object_aabb": (None, [C.c_void_p, C.c_int, f32p]),
     }
     if with_desc:
+        api[f"{p}_defer_mesh_bvh"] = (None, [C.c_void_p, C.c_int])
         api[f"{p}_scene_desc"] = (C.POINTER(mrt_scene_desc), [C.c_void_p])
         api[f"{p}_scene_camera"] = (C.POINTER(mrt_camera), [C.c_void_p])
     return api

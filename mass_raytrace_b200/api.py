@@ -293,9 +293,12 @@ def _f3(v):
 
 
 class NativeScene:
-    """Replays a (World, Camera) into a native scene builder. backend = (ctypes lib, symbol prefix)."""
+    """Replays a (World, Camera) into a native scene builder. backend = (ctypes lib, symbol prefix).
 
-    def __init__(self, world: World, camera: Optional[Camera] = None, backend=None):
+    defer_mesh_bvh: meshes carry no reference-topology tree (mrth_defer_mesh_bvh, include/mrt_host.h) — the load-time
+    saving for a scene that is rendered without MRT_SCENE_KEEP_TOPOLOGY; host library only."""
+
+    def __init__(self, world: World, camera: Optional[Camera] = None, backend=None, defer_mesh_bvh: bool = False):
         if backend is None:
             backend = (_ffi.host_lib(), "mrth")
         self.lib, self.prefix = backend
@@ -308,6 +311,8 @@ class NativeScene:
         self.mesh_max_abs = {}
         self.object_ids = []
         self._fn("seed")(self._h, world.bvh_seed)
+        if defer_mesh_bvh:
+            self._fn("defer_mesh_bvh")(self._h, 1)
         self._background(world.background)
         for obj in world.objects:
             self.object_ids.append(self._add(obj))

@@ -973,9 +973,13 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     const bool keep = (s->flags & MRT_SCENE_KEEP_TOPOLOGY) != 0;
     for (uint64_t i = 0; i < s->n_blas; ++i) {
         const mrt_blas& b = s->blas[i];
-        if (MRT_REF_KIND(b.root) != MRT_PRIM_NODE || MRT_REF_INDEX(b.root) >= s->n_nodes || (uint64_t)b.first_tri + b.n_tris > s->n_tris)
-            return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
-        if (!keep) continue;  // the SAH rebuild reads the BLAS's triangle range only, never the caller's nodes
+        if ((uint64_t)b.first_tri + b.n_tris > s->n_tris) return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
+        if (b.root == MRT_REF_NONE) {  // a mesh without a caller tree (mrth_defer_mesh_bvh)
+            if (keep) return fail(ctx, MRT_E_INVALID, "MRT_SCENE_KEEP_TOPOLOGY needs the nodes of every BLAS");
+            continue;
+        }
+        if (MRT_REF_KIND(b.root) != MRT_PRIM_NODE || MRT_REF_INDEX(b.root) >= s->n_nodes) return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
+        if (!keep) continue;  // the rebuild reads the BLAS's triangle range only, never the caller's nodes
         int d = subtree_depth(s, b.root, false, why);
         if (d < 0) return fail(ctx, MRT_E_INVALID, why);
         blas_depth = std::max(blas_depth, d);

@@ -9,6 +9,8 @@
 #include "mrt_host.h"
 
 #include <algorithm>
+#include <array>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -16,6 +18,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -112,6 +115,31 @@ struct BuildItem {
     float lo[3], hi[3];
 };
 
+// Allocator whose resize() leaves new elements uninitialised, so the threads that fill a big mesh are also the ones that
+// touch its pages first (a value-initialising resize would fault all of them in on one thread).
+template <class T>
+struct RawAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = RawAlloc<U>; };
+    template <class U, class... A>
+    void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+
+// fn(first, last) over [0, n) on up to 16 threads; small ranges stay on the caller's thread
+template <class F>
+void host_parallel_for(size_t n, F&& fn) {
+    const size_t kGrain = 1u << 15;
+    size_t threads = std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), 16, n / kGrain});
+    if (threads <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const size_t chunk = (n + threads - 1) / threads;
+    for (size_t t = 1; t < threads; ++t) pool.emplace_back([=, &fn] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    fn((size_t)0, std::min(n, chunk));
+    for (auto& th : pool) th.join();
+}
+
 }  // namespace
 
 struct mrth_scene {
@@ -123,9 +151,11 @@ struct mrth_scene {
     std::vector<mrt_material> materials;
     std::vector<mrt_node> nodes;
     std::vector<mrt_sphere> spheres;
-    std::vector<float> tri_verts;
-    std::vector<mrt_tri_shading> tri_shading;
+    std::vector<float, RawAlloc<float>> tri_verts;
+    std::vector<mrt_tri_shading, RawAlloc<mrt_tri_shading>> tri_shading;
     std::vector<mrt_blas> blas;
+    std::vector<std::array<float, 6>> blas_box;  // Model bounding box (= root node box) per mesh, kept apart so a deferred mesh has one too
+    bool defer_mesh_bvh = false;                 // mrth_defer_mesh_bvh
     std::vector<mrt_instance> instances;
     std::vector<mrt_volume> volumes;
     std::vector<uint32_t> objects;  // World.objects in add order (prim refs)
@@ -212,32 +242,61 @@ uint32_t build_bvh(mrth_scene& s, std::vector<BuildItem>& items, size_t first, s
 
 int finish_mesh(mrth_scene* s, uint32_t first_tri, uint32_t n_tris) {
     if (n_tris == 0) { s->err = "mesh has no triangles"; return MRT_E_INVALID; }
-    std::vector<BuildItem> items(n_tris);
-    for (uint32_t i = 0; i < n_tris; ++i) {
-        items[i].ref = MRT_REF(MRT_PRIM_TRIANGLE, first_tri + i);
-        prim_bounds(*s, items[i].ref, items[i].lo, items[i].hi);
-    }
-    const size_t before = s->nodes.size();
     mrt_blas b;
-    b.root = build_bvh(*s, items, 0, n_tris);
     b.first_tri = first_tri;
     b.n_tris = n_tris;
-    b.n_nodes = (uint32_t)(s->nodes.size() - before);
+    std::array<float, 6> box;
+    if (s->defer_mesh_bvh) {
+        // No reference-topology tree: the backend builds its own over [first_tri, first_tri + n_tris). The box is the
+        // min / max over the vertices, which is what the joins up the reference tree (geom.rs:249-254) arrive at too.
+        box = {kInf, kInf, kInf, -kInf, -kInf, -kInf};
+        const float* v = &s->tri_verts[9 * (size_t)first_tri];
+        std::vector<std::array<float, 6>> parts(17, box);
+        std::atomic<int> slot{0};
+        host_parallel_for(3 * (size_t)n_tris, [&](size_t a, size_t e) {
+            std::array<float, 6> bb = {kInf, kInf, kInf, -kInf, -kInf, -kInf};
+            for (size_t i = a; i < e; ++i)
+                for (int k = 0; k < 3; ++k) {  // f32::min / max with a non-NaN accumulator: a NaN coordinate is skipped either way
+                    const float x = v[3 * i + k];
+                    bb[k] = x < bb[k] ? x : bb[k];
+                    bb[3 + k] = x > bb[3 + k] ? x : bb[3 + k];
+                }
+            parts[(size_t)slot.fetch_add(1)] = bb;
+        });
+        for (const auto& bb : parts)
+            for (int k = 0; k < 3; ++k) {
+                box[k] = bb[k] < box[k] ? bb[k] : box[k];
+                box[3 + k] = bb[3 + k] > box[3 + k] ? bb[3 + k] : box[3 + k];
+            }
+        b.root = MRT_REF_NONE;
+        b.n_nodes = 0;
+    } else {
+        std::vector<BuildItem> items(n_tris);
+        for (uint32_t i = 0; i < n_tris; ++i) {
+            items[i].ref = MRT_REF(MRT_PRIM_TRIANGLE, first_tri + i);
+            prim_bounds(*s, items[i].ref, items[i].lo, items[i].hi);
+        }
+        const size_t before = s->nodes.size();
+        b.root = build_bvh(*s, items, 0, n_tris);
+        b.n_nodes = (uint32_t)(s->nodes.size() - before);
+        const mrt_node& root = s->nodes[MRT_REF_INDEX(b.root)];
+        box = {root.bmin[0], root.bmin[1], root.bmin[2], root.bmax[0], root.bmax[1], root.bmax[2]};
+    }
     s->blas.push_back(b);
+    s->blas_box.push_back(box);
     return (int)s->blas.size() - 1;
 }
 
 // Triangle::new geom.rs:449-466
-void push_flat_triangle(mrth_scene* s, Vec3 a, Vec3 b, Vec3 c, int material) {
-    float v[9];
+void flat_triangle_at(mrth_scene* s, size_t i, Vec3 a, Vec3 b, Vec3 c, int material) {
+    float* v = &s->tri_verts[9 * i];
     store3(v, a); store3(v + 3, b); store3(v + 6, c);
-    s->tri_verts.insert(s->tri_verts.end(), v, v + 9);
     Vec3 n = normalize(cross3(sub(b, a), sub(c, a)));
     mrt_tri_shading sh{};
     store3(sh.normal, n); store3(sh.normal + 3, n); store3(sh.normal + 6, n);
     sh.material = material;
     sh.flags = 0;
-    s->tri_shading.push_back(sh);
+    s->tri_shading[i] = sh;
 }
 
 int push_object(mrth_scene* s, uint32_t ref) {
@@ -554,6 +613,7 @@ mrth_scene* mrth_scene_new(void) {
 void mrth_scene_free(mrth_scene* s) { delete s; }
 const char* mrth_last_error(mrth_scene* s) { return s->err.c_str(); }
 void mrth_seed(mrth_scene* s, uint64_t seed) { s->rng.state = seed; }
+void mrth_defer_mesh_bvh(mrth_scene* s, int on) { s->defer_mesh_bvh = on != 0; }
 float mrth_rand_f32(mrth_scene* s) { return s->rng.f32(); }
 
 int mrth_surface_solid(mrth_scene* s, float r, float g, float b, float a) { return push_surface(s, MRT_SURF_SOLID, -1, -1, 0, r, g, b, a); }
@@ -618,9 +678,11 @@ int mrth_mesh_new(mrth_scene* s, const float* v, uint64_t n, int tri_material) {
     if (!valid_material(s, tri_material, false)) return MRT_E_INVALID;
     if (n == 0 || n > 0x1FFFFFFFull - s->tri_shading.size()) { s->err = "triangle count out of range"; return MRT_E_INVALID; }
     uint32_t first = (uint32_t)s->tri_shading.size();
-    s->tri_verts.reserve(s->tri_verts.size() + 9 * n);
-    s->tri_shading.reserve(s->tri_shading.size() + n);
-    for (uint64_t i = 0; i < n; ++i) push_flat_triangle(s, load3(v + 9 * i), load3(v + 9 * i + 3), load3(v + 9 * i + 6), tri_material);
+    s->tri_verts.resize(s->tri_verts.size() + 9 * n);  // uninitialised (RawAlloc): every element is written below
+    s->tri_shading.resize(s->tri_shading.size() + n);
+    host_parallel_for((size_t)n, [&](size_t a, size_t e) {
+        for (size_t i = a; i < e; ++i) flat_triangle_at(s, first + i, load3(v + 9 * i), load3(v + 9 * i + 3), load3(v + 9 * i + 6), tri_material);
+    });
     return finish_mesh(s, first, (uint32_t)n);
 }
 int mrth_mesh_new_uv(mrth_scene* s, const float* v, const float* nn, const float* uv, uint64_t n, int tri_material) {
@@ -725,14 +787,15 @@ static int add_instance_common(mrth_scene* s, int mesh, const Mat4& fwd, const M
     mrt_instance in{};
     std::memcpy(in.transform, fwd.m, 64);
     std::memcpy(in.inv_transform, inv.m, 64);
-    const mrt_node& root = s->nodes[MRT_REF_INDEX(s->blas[(size_t)mesh].root)];
+    const float* root_min = s->blas_box[(size_t)mesh].data();
+    const float* root_max = root_min + 3;
     if (flags & MRT_INSTANCE_IDENTITY) {  // Model::bounding_box geom.rs:330-332
-        std::memcpy(in.bmin, root.bmin, 12);
-        std::memcpy(in.bmax, root.bmax, 12);
+        std::memcpy(in.bmin, root_min, 12);
+        std::memcpy(in.bmax, root_max, 12);
     } else {  // geom.rs:369-381 with corners() :256-272
         float lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
         for (int c = 0; c < 8; ++c) {
-            Vec3 corner{(c & 1) ? root.bmin[0] : root.bmax[0], (c & 2) ? root.bmin[1] : root.bmax[1], (c & 4) ? root.bmin[2] : root.bmax[2]};
+            Vec3 corner{(c & 1) ? root_min[0] : root_max[0], (c & 2) ? root_min[1] : root_max[1], (c & 4) ? root_min[2] : root_max[2]};
             Vec3 p = mat_apply(fwd, corner, 1.0f);
             lo[0] = std::fmin(lo[0], p.x); lo[1] = std::fmin(lo[1], p.y); lo[2] = std::fmin(lo[2], p.z);
             hi[0] = std::fmax(hi[0], p.x); hi[1] = std::fmax(hi[1], p.y); hi[2] = std::fmax(hi[2], p.z);

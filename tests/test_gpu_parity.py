@@ -716,3 +716,30 @@ def test_device_built_bvh(renderer, mesh_ply):
         assert ((g2["object"] == 0) & (g2["t"] > 1.3 * near)).sum() > 1000  # rays that went through a hole and hit the far inside of the sphere
     finally:
         renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)
+
+
+def test_scene_without_mesh_trees(renderer, mesh_ply):
+    """mrth_defer_mesh_bvh (include/mrt_host.h): the host skips Model::new's median-split build and hands over mrt_blas.root =
+    MRT_REF_NONE. The backend builds every BLAS from the triangle range itself (host SAH or GPU LBVH), so primary rays must match the
+    oracle exactly as before; asking to keep a topology that is not there is an error, and leaves the uploaded scene in place."""
+    path, md, n = mesh_ply
+    world, camera = scenes.lucy_layout(path, md, grid=1)  # 9 instances of one 65,536-triangle mesh + ground cube + sun sphere
+    o = OracleScene(world, camera).render_aov(480, 270)
+    lazy = NativeScene(world, camera, defer_mesh_bvh=True)
+    assert lazy.desc().contents.n_nodes < 64  # the TLAS only
+    try:
+        for mode in (0, 1):
+            renderer.set_option(renderer.OPT_DEVICE_BUILD, mode)
+            renderer.set_scene(lazy)
+            g = renderer.render_aov(480, 270)
+            check_aov(g, o)
+            assert (g["tri"] != NONE).mean() > 0.3
+        with pytest.raises(RuntimeError, match="KEEP_TOPOLOGY"):
+            renderer.set_scene(lazy, keep_topology=True)
+        check_aov(renderer.render_aov(480, 270), o)
+        rgb, bounces, _ = renderer.render(160, 90, 8, 50, seed=3)
+        renderer.set_scene(NativeScene(world, camera))
+        rgb_ref, bounces_ref, _ = renderer.render(160, 90, 8, 50, seed=3)
+        assert (bounces == bounces_ref).mean() > 0.999 and np.abs(rgb - rgb_ref).max(-1).mean() < 1e-3
+    finally:
+        renderer.set_option(renderer.OPT_DEVICE_BUILD, 1)

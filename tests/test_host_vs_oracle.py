@@ -171,3 +171,43 @@ def test_uv_mesh_and_textures_flatten(scene_pairs):
     assert 0.0 <= tex.min() and tex.max() <= 1.0 and tex[3] == 1.0
     assert len(d["volumes"]) == 2 and np.isclose(d["volumes"]["neg_inv_density"][0], -5.0)
     assert any(i["flags"] == 1 for i in d["instances"])  # the Model (identity instance) holding the textured sphere
+
+
+@pytest.mark.parametrize("name", ["cornell", "lucy", "book2"])
+def test_deferred_mesh_bvh_keeps_everything_but_the_mesh_nodes(tmp_mesh_dir, name):
+    """mrth_defer_mesh_bvh (include/mrt_host.h): no reference-topology tree per mesh. Triangles, shading records, instance matrices
+    and instance boxes (Model::bounding_box / Instance::new, geom.rs:330-332, 369-381, from the mesh box) must not change; only the
+    BLAS nodes go, and the TLAS is still a consistent tree over every object."""
+    world, camera = _scene_list(tmp_mesh_dir)[name]
+    ref, lazy = NativeScene(world, camera), NativeScene(world, camera, defer_mesh_bvh=True)
+    a, b = desc_arrays(ref), desc_arrays(lazy)
+    assert np.array_equal(a["tri_verts"], b["tri_verts"]) and a["shading"].tobytes() == b["shading"].tobytes()
+    assert a["spheres"].tobytes() == b["spheres"].tobytes() and a["volumes"].tobytes() == b["volumes"].tobytes()
+    assert a["instances"].tobytes() == b["instances"].tobytes()  # transforms, world boxes, BLAS index, material, object id
+    assert len(b["blas"]) == len(a["blas"]) > 0
+    for x, y in zip(a["blas"], b["blas"]):
+        assert (int(y["first_tri"]), int(y["n_tris"])) == (int(x["first_tri"]), int(x["n_tris"]))
+        assert int(y["root"]) == 0xFFFFFFFF and int(y["n_nodes"]) == 0
+    n_blas_nodes = int(sum(int(x["n_nodes"]) for x in a["blas"]))
+    assert len(b["nodes"]) == len(a["nodes"]) - n_blas_nodes
+    for m in range(len(b["blas"])):
+        assert lazy._fn("mesh_node_count")(lazy._h, m) == 0
+    # the TLAS: every object exactly once, boxes joined bottom-up
+    seen = []
+
+    def walk(r):
+        kind, idx = r >> 29, r & 0x1FFFFFFF
+        if kind != 0:
+            seen.append(r)
+            return _bounds(b, r)
+        n = b["nodes"][idx]
+        lo, hi = walk(int(n["left"]))
+        if n["right"] != 0xFFFFFFFF:
+            lo2, hi2 = walk(int(n["right"]))
+            lo, hi = np.minimum(lo, lo2), np.maximum(hi, hi2)
+        assert np.array_equal(n["bmin"], lo.astype(np.float32)) and np.array_equal(n["bmax"], hi.astype(np.float32))
+        return lo, hi
+
+    assert len(b["roots"]) == 1
+    walk(b["roots"][0])
+    assert len(seen) == len(set(seen)) == len(world.objects)
