@@ -256,6 +256,9 @@ int mrt_accum_download(mrt_context* ctx, float* sum_rgb, uint32_t* sum_bounces, 
  * mode: 0 Default, 2 Depth (mode numbers follow DisplayMode, main.rs:534-541; Denoise=1 is treated as Default). out: w*h*3 bytes. */
 int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8_t* out_rgb);
 
+/* DisplayMode main.rs:534-541 */
+enum { MRT_DISPLAY_DEFAULT = 0, MRT_DISPLAY_DENOISE = 1, MRT_DISPLAY_DEPTH = 2, MRT_DISPLAY_ALBEDO = 3, MRT_DISPLAY_NORMAL = 4 };
+
 /* knobs and counters (the reference only prints whole seconds, main.rs:270) */
 enum {
     MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */

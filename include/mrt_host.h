@@ -82,6 +82,13 @@ void mrth_get_camera(mrth_scene*, float out19[19]);
 void mrth_get_instance(mrth_scene*, int object, float transform16[16], float inv16[16], float aabb6[6]);
 void mrth_get_object_aabb(mrth_scene*, int object, float aabb6[6]);
 
+/* Image export (main.rs:640-783). mrt_resolve_rgb8 covers Default / Denoise / Depth on the device image; the two FloatBuffer modes
+ * work on the host buffers mrt_render_aov filled: Albedo = clamp(p, 0, 1)^(1/2.2), Normal = (p + 1) / 2, then `(f * 255) as u8`.
+ * flip != 0 reverses the rows like Image::dump. mode: MRT_DISPLAY_ALBEDO or MRT_DISPLAY_NORMAL. */
+int mrth_float_buffer_rgb8(const float* rgb, uint32_t w, uint32_t h, int mode, int flip, uint8_t* out_rgb);
+/* Image::dump's file: creates the parent directories, writes an 8-bit RGB PNG (rows as given). */
+int mrth_write_png(const char* path, const uint8_t* rgb, uint32_t w, uint32_t h);
+
 /* the flatten() walk: valid until the scene is mutated or freed */
 const mrt_scene_desc* mrth_scene_desc(mrth_scene*);
 const mrt_camera* mrth_scene_camera(mrth_scene*);

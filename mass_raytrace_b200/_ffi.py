@@ -138,6 +138,8 @@ def scene_api(prefix, with_desc):
 
 
 HOST_API = scene_api("mrth", with_desc=True)
+HOST_API["mrth_float_buffer_rgb8"] = (C.c_int, [f32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, u8p])
+HOST_API["mrth_write_png"] = (C.c_int, [C.c_char_p, u8p, C.c_uint32, C.c_uint32])
 
 
 def bind(lib, api):

@@ -14,6 +14,7 @@ libmrt_host.so (which flattens to mrt_scene_desc), or, in tests only, the CPU or
 All geometry arithmetic (triangle normals, instance matrices, BVH build, camera frame, PLY parsing) happens natively.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence, Tuple
 
@@ -612,6 +613,30 @@ class Renderer:
 
     def synchronize(self):
         self._check(self.lib.mrt_synchronize(self._h), "mrt_synchronize")
+
+
+DISPLAY_DEFAULT, DISPLAY_DENOISE, DISPLAY_DEPTH, DISPLAY_ALBEDO, DISPLAY_NORMAL = range(5)  # DisplayMode main.rs:534-541
+
+
+def float_buffer_rgb8(buf, mode, flip=True):
+    """Image::to_rgb_bytes(Albedo | Normal) over one of render_aov's FloatBuffers (main.rs:694-721); flip reverses rows like dump()."""
+    a = np.ascontiguousarray(buf, dtype=np.float32)
+    h, w = a.shape[:2]
+    out = np.zeros((h, w, 3), np.uint8)
+    rc = _ffi.host_lib().mrth_float_buffer_rgb8(a.ctypes.data_as(_ffi.f32p), w, h, mode, 1 if flip else 0, out.ctypes.data_as(_ffi.u8p))
+    if rc < 0:
+        raise ValueError(f"mrth_float_buffer_rgb8: error {rc} (mode must be DISPLAY_ALBEDO or DISPLAY_NORMAL)")
+    return out
+
+
+def write_png(path, rgb8):
+    """Image::dump's file (main.rs:770-783): parent directories created, 8-bit RGB PNG, rows as given."""
+    a = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w = a.shape[:2]
+    if a.shape != (h, w, 3):
+        raise ValueError("write_png wants an (h, w, 3) uint8 image")
+    if _ffi.host_lib().mrth_write_png(os.fsencode(path), a.ctypes.data_as(_ffi.u8p), w, h) < 0:
+        raise OSError(f"unable to save image {path}")
 
 
 def render(world: World, camera: Camera, width, height, spp, max_depth=50, seed=1, device=0):

@@ -21,6 +21,9 @@
 #include <thread>
 #include <vector>
 
+#include <cerrno>
+#include <sys/stat.h>
+
 namespace {
 
 const float kPi = 3.14159265358979323846f;
@@ -600,6 +603,7 @@ int mesh_from_uv_faces(mrth_scene* s, const float* v, const float* nn, const flo
 }
 
 #include "mrt_obj.inc"
+#include "mrt_png_write.inc"
 
 }  // namespace
 
@@ -885,6 +889,39 @@ void mrth_get_instance(mrth_scene* s, int object, float tf[16], float inv[16], f
     std::memcpy(aabb + 3, in.bmax, 12);
 }
 void mrth_get_object_aabb(mrth_scene* s, int object, float aabb[6]) { prim_bounds(*s, s->objects.at((size_t)object), aabb, aabb + 3); }
+
+// Image::to_rgb_bytes(Albedo | Normal) over a FloatBuffer (main.rs:694-721, final cast :718-721), rows reversed like dump (:763-768) when flip != 0
+int mrth_float_buffer_rgb8(const float* buf, uint32_t w, uint32_t h, int mode, int flip, uint8_t* out) {
+    if (!buf || !out || w == 0 || h == 0) return MRT_E_INVALID;
+    if (mode != MRT_DISPLAY_ALBEDO && mode != MRT_DISPLAY_NORMAL) return MRT_E_UNSUPPORTED;
+    const size_t stride = (size_t)w * 3;
+    for (uint32_t y = 0; y < h; ++y) {
+        const float* src = buf + stride * y;
+        uint8_t* dst = out + stride * (flip ? h - 1 - y : y);
+        for (size_t i = 0; i < stride; ++i) {
+            const float p = src[i];
+            // f32::min / max return the other operand for a NaN: a NaN albedo becomes 1.0, a NaN normal stays NaN and casts to 0
+            const float f = mode == MRT_DISPLAY_ALBEDO ? std::pow(std::fmax(std::fmin(p, 1.0f), 0.0f), 1.0f / 2.2f) : (p + 1.0f) / 2.0f;
+            dst[i] = saturate_u8(f * 255.0f);
+        }
+    }
+    return MRT_OK;
+}
+
+// Image::dump's file (main.rs:770-783): parent directories created, 8-bit RGB PNG, rows as given (resolve with flip != 0 first)
+int mrth_write_png(const char* path, const uint8_t* rgb, uint32_t w, uint32_t h) {
+    if (!path || !rgb || w == 0 || h == 0 || (uint64_t)w * h > (1ull << 28)) return MRT_E_INVALID;
+    std::vector<uint8_t> file;
+    png_encode_rgb8(rgb, w, h, file);
+    FILE* f = create_parent_dirs(path) ? std::fopen(path, "wb") : nullptr;
+    bool ok = f && std::fwrite(file.data(), 1, file.size(), f) == file.size();
+    if (f) ok = std::fclose(f) == 0 && ok;
+    if (!ok) {
+        std::fprintf(stderr, "Unable to save image: %s: %s\n", path, std::strerror(errno));  // main.rs:780-782: reported, not fatal
+        return MRT_E_INVALID;
+    }
+    return MRT_OK;
+}
 
 const mrt_scene_desc* mrth_scene_desc(mrth_scene* s) {
     mrt_scene_desc& d = s->desc;

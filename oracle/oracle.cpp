@@ -1718,6 +1718,19 @@ void orc_resolve_rgb8(const float* sum_rgb, uint32_t w, uint32_t h, uint32_t cou
     }
 }
 
+void orc_float_buffer_rgb8(const float* buf, uint32_t w, uint32_t h, int mode, int flip, uint8_t* out) {  // main.rs:694-721, 760-768
+    for (uint32_t y = 0; y < h; ++y) {
+        uint32_t sy = flip ? (h - 1 - y) : y;
+        for (uint32_t x = 0; x < w * 3; ++x) {
+            F p = buf[(size_t)sy * w * 3 + x];
+            F f = mode == 3 ? std::pow(fmax_(fmin_(p, 1.0f), 0.0f), 1.0f / 2.2f)  // Albedo :694-697
+                            : (p + 1.0f) / 2.0f;                                  // Normal :708-711
+            F v = f * 255.0f;
+            out[(size_t)y * w * 3 + x] = (uint8_t)(v >= 255.0f ? 255 : (v > 0.0f ? (int)v : 0));
+        }
+    }
+}
+
 // ----------------------------- known-answer hooks ----------------------------------------------
 int orc_kat_sphere(float cx, float cy, float cz, float r, const float o[3], const float d[3], float tmin, float tmax, float out[8]) {
     static Absorb m;

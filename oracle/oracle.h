@@ -111,6 +111,8 @@ void orc_render(orc_scene*, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_d
                 float* sum_rgb, uint32_t* sum_bounces, orc_counters* counters);
 /* Image::to_rgb_bytes(Default) + dump row flip (main.rs:640-722, 760-768): count merges -> RGB8 top row first when flip!=0 */
 void orc_resolve_rgb8(const float* sum_rgb, uint32_t w, uint32_t h, uint32_t count, int flip, uint8_t* out);
+/* Image::to_rgb_bytes(Albedo = 3 | Normal = 4) over a FloatBuffer (main.rs:694-721), rows reversed when flip != 0 */
+void orc_float_buffer_rgb8(const float* rgb, uint32_t w, uint32_t h, int mode, int flip, uint8_t* out);
 
 /* single-call hooks for known-answer tests */
 int  orc_kat_sphere(float cx, float cy, float cz, float r, const float o[3], const float d[3], float tmin, float tmax, float out8[8]); /* t, p3, n3, front */

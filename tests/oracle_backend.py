@@ -23,6 +23,7 @@ _EXTRA = {
     "orc_render_aov": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _ffi.f32p, _ffi.f32p, _ffi.u32p, _ffi.u32p, _ffi.f32p, C.POINTER(orc_counters)]),
     "orc_render": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _ffi.f32p, _ffi.u32p, C.POINTER(orc_counters)]),
     "orc_resolve_rgb8": (None, [_ffi.f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _ffi.u8p]),
+    "orc_float_buffer_rgb8": (None, [_ffi.f32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _ffi.u8p]),
     "orc_register_png": (None, [C.c_void_p, C.c_char_p, _ffi.u8p, C.c_uint32, C.c_uint32]),
     "orc_kat_sphere": (C.c_int, [C.c_float] * 4 + [C.POINTER(f3), C.POINTER(f3), C.c_float, C.c_float, _ffi.f32p]),
     "orc_kat_aabb": (C.c_int, [C.POINTER(f3)] * 4 + [C.c_float, C.c_float]),
