@@ -1,14 +1,16 @@
 /* A host in plain C: the Cornell box of the reference (src/scenes/cornell.rs:29-99) built through libmrt_host.so, rendered through
- * libmrt_cuda.so, written as a binary PPM. Nothing but the two C headers is used -- this is the call sequence a foreign-language
- * host (the reference's Rust main.rs) goes through, and the program the parity suite runs to check that the
- * boundary gives the same image whichever language drives it (tests/test_c_host.py).
+ * libmrt_cuda.so, written as a binary PPM (or a PNG when the output name ends in .png). Nothing but the two C headers is used --
+ * this is the call sequence a foreign-language host (the reference's Rust main.rs) goes through, and the
+ * program the parity suite runs to check that the boundary gives the same image whichever language drives it
+ * (tests/test_c_host.py).
  *
  *   cc -std=c11 -I include examples/cornell.c -L mass_raytrace_b200 -lmrt_host -lmrt_cuda -lm -o cornell
- *   ./cornell mass_raytrace_b200/assets/cube.ply 512 512 64 out.ppm
+ *   ./cornell mass_raytrace_b200/assets/cube.ply 512 512 64 out.png
  */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "mrt.h"
 #include "mrt_host.h"
@@ -31,7 +33,7 @@ static int add_cube(mrth_scene* s, int cube, float tx, float ty, float tz, float
 
 int main(int argc, char** argv) {
     if (argc < 6) {
-        fprintf(stderr, "usage: %s cube.ply width height spp out.ppm\n", argv[0]);
+        fprintf(stderr, "usage: %s cube.ply width height spp out.ppm|out.png\n", argv[0]);
         return 1;
     }
     const char* ply = argv[1];
@@ -84,19 +86,24 @@ int main(int argc, char** argv) {
 
     mrt_stats st;
     if (mrt_get_stats(ctx, &st) != MRT_OK) return die_ctx(ctx, "mrt_get_stats");
-    uint64_t hash = 1469598103934665603ull; /* FNV-1a over the rgb8 image */
+    uint64_t hash = 14695981039346656037ull; /* FNV-1a over the rgb8 image */
     for (size_t i = 0; i < (size_t)w * h * 3; ++i) hash = (hash ^ rgb[i]) * 1099511628211ull;
     printf("paths %llu rays %llu render_ms %.3f fnv1a %016llx\n", (unsigned long long)st.paths, (unsigned long long)st.rays, st.render_ms,
            (unsigned long long)hash);
 
-    FILE* f = fopen(argv[5], "wb");
-    if (!f) {
-        perror(argv[5]);
-        return 5;
+    const size_t len = strlen(argv[5]);
+    if (len > 4 && strcmp(argv[5] + len - 4, ".png") == 0) { /* Image::dump main.rs:760-783 */
+        if (mrth_write_png(argv[5], rgb, w, h) != MRT_OK) return 5;
+    } else {
+        FILE* f = fopen(argv[5], "wb");
+        if (!f) {
+            perror(argv[5]);
+            return 5;
+        }
+        fprintf(f, "P6\n%u %u\n255\n", w, h);
+        fwrite(rgb, 1, (size_t)w * h * 3, f);
+        fclose(f);
     }
-    fprintf(f, "P6\n%u %u\n255\n", w, h);
-    fwrite(rgb, 1, (size_t)w * h * 3, f);
-    fclose(f);
     free(rgb);
     mrt_context_destroy(ctx);
     mrth_scene_free(s);
