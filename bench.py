@@ -313,12 +313,19 @@ def main():
             traffic = per_ray_dram * rays_local / max(ext_launches, 1) if per_ray_dram else None
         except Exception:
             traffic = None
+    limiter = None  # the ncu view of the same kernel (issue slots, lanes per instruction): static figures of the committed captures
+    try:
+        limiter = json.load(open(os.path.join(ROOT, "profiles", "extend_issue.json"))).get(args.workload)
+    except Exception:
+        limiter = None
     roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "alg_bytes_per_ray": b_ray, "per_ray": per_ray, "rays_per_launch": rays_local / max(ext_launches, 1),
                 "mean_launch_ms": ext_ms / max(ext_launches, 1), "extend_share_of_step": ext_ms / sum(tstep_ms),
                 "shade_share_of_step": sum(s["shade_ms"] for s in tstats) / sum(tstep_ms),
                 "generate_share_of_step": sum(s["generate_ms"] for s in tstats) / sum(tstep_ms),
-                "note": "algorithmic bytes are served mostly by L1/L2 when the acceleration structure is cache-resident, so achieved can exceed the HBM peak"}
+                "ncu_limiter": limiter,
+                "note": "algorithmic bytes are served mostly by L1/L2 when the acceleration structure is cache-resident, so achieved can exceed the HBM peak; "
+                        "the kernel is issue-bound on divergent code (ncu_limiter)"}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------------
     out_rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
