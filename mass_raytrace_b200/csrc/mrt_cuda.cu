@@ -974,6 +974,7 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     for (uint64_t i = 0; i < s->n_blas; ++i) {
         const mrt_blas& b = s->blas[i];
         if ((uint64_t)b.first_tri + b.n_tris > s->n_tris) return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
+        if (b.n_tris == 0) return fail(ctx, MRT_E_INVALID, "BLAS without triangles (BvhNode::new does not terminate on an empty list, geom.rs:130-144)");
         if (b.root == MRT_REF_NONE) {  // a mesh without a caller tree (mrth_defer_mesh_bvh)
             if (keep) return fail(ctx, MRT_E_INVALID, "MRT_SCENE_KEEP_TOPOLOGY needs the nodes of every BLAS");
             continue;
@@ -994,6 +995,13 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
         if (d == -2) return fail(ctx, MRT_E_UNSUPPORTED, why);
         if (d < 0) return fail(ctx, MRT_E_INVALID, why);
         tlas_depth = std::max(tlas_depth, d);
+    }
+    if (keep) {  // every node is converted below, reachable from a root or not: all of them must name children that exist
+        for (uint64_t i = 0; i < s->n_nodes; ++i) {
+            const mrt_node& n = s->nodes[i];
+            if (n.left == MRT_REF_NONE || !ref_ok(s, n.left, true) || (n.right != MRT_REF_NONE && !ref_ok(s, n.right, true)))
+                return fail(ctx, MRT_E_INVALID, "node " + std::to_string(i) + ": child reference out of range");
+        }
     }
     if (keep && tlas_depth + blas_depth + 2 > kStackSize)
         return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack");

@@ -129,7 +129,10 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.96
 struct Rand4 {
     float x, y, z, w;
 };
-enum : uint32_t { kStreamScatter = 0, kStreamVolume = 0x100, kStreamMix = 0x200, kStreamEmit = 0x300, kStreamAlpha = 0x400 };
+// Stream ids: the KIND of draw sits in the top four bits and the index (volume number, Mix nesting level, triangle) below them, so
+// that two different uses at the same (pixel, sample, bounce) can never share a counter whatever the index is.
+enum : uint32_t { kStreamScatter = 0u << 28, kStreamVolume = 1u << 28, kStreamMix = 2u << 28, kStreamEmit = 3u << 28, kStreamAlpha = 4u << 28 };
+constexpr uint32_t kStreamIndexMask = (1u << 28) - 1u;
 constexpr uint32_t kBounceCamera = 0xFFFFFFFFu;
 struct RngKey {
     uint32_t pixel, sample, bounce;
@@ -424,7 +427,7 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
             if (VOLUME) {
                 if (COUNT) cnt->volume_tests++;
                 mrt_volume vol = sc.volumes[idx];
-                Rand4 xi = draw4(key, kStreamVolume + idx);
+                Rand4 xi = draw4(key, kStreamVolume | (idx & kStreamIndexMask));
                 float t;
                 if (volume_test(sc, vol, T.r, t_min, T.best.t, xi.x, t)) T.best = HitRec{t, ref, kNone};
             }
@@ -544,7 +547,7 @@ __device__ __noinline__ bool triangle_alpha_test(const DScene& sc, const DTriVer
     mrt_material mat = sc.materials[sh.material];
     uint32_t level = 0;
     while (mat.kind == MRT_MAT_MIX && level < 16) {
-        Rand4 c = draw4(key, kStreamAlpha + ((tri_dev & 0xFFFFu) << 4) + level);
+        Rand4 c = draw4(key, kStreamAlpha | ((tri_dev & 0xFFFFFFu) << 4) | level);  // level < 16
         mat = sc.materials[(c.x < mat.p[0]) ? mat.left : mat.right];
         ++level;
     }

@@ -710,8 +710,19 @@ int mrth_mesh_load_obj_with(mrth_scene* s, const char* path, int tri_material) {
     if (!valid_material(s, tri_material, false)) return MRT_E_INVALID;
     return load_obj(s, path, ObjOptions{false, MRT_WRAP_REPEAT, tri_material, {}});
 }
+// a bad handle sets the error text and returns (nothing unwinds across the C boundary)
+static const mrt_blas* mesh_or_null(mrth_scene* s, int mesh) {
+    if (mesh < 0 || (size_t)mesh >= s->blas.size()) { s->err = "mesh handle out of range"; return nullptr; }
+    return &s->blas[(size_t)mesh];
+}
+static bool object_ok(mrth_scene* s, int object) {
+    if (object < 0 || (size_t)object >= s->objects.size()) { s->err = "object index out of range"; return false; }
+    return true;
+}
 void mrth_mesh_get_shading(mrth_scene* s, int mesh, float* normals9, float* uvs6, int32_t* materials) {
-    const mrt_blas& b = s->blas.at((size_t)mesh);
+    const mrt_blas* bp = mesh_or_null(s, mesh);
+    if (!bp) return;
+    const mrt_blas& b = *bp;
     for (uint32_t i = 0; i < b.n_tris; ++i) {
         const mrt_tri_shading& sh = s->tri_shading[(size_t)b.first_tri + i];
         if (normals9) std::memcpy(normals9 + 9 * (size_t)i, sh.normal, 36);
@@ -772,12 +783,20 @@ int mrth_mesh_load_stl(mrth_scene* s, const char* path, const int perm[3], int t
     if (!ok) { s->err = "stl read error"; return MRT_E_INVALID; }
     return mrth_mesh_new(s, v.data(), v.size() / 9, tri_material);
 }
-uint64_t mrth_mesh_tri_count(mrth_scene* s, int mesh) { return s->blas.at((size_t)mesh).n_tris; }
+uint64_t mrth_mesh_tri_count(mrth_scene* s, int mesh) {
+    const mrt_blas* b = mesh_or_null(s, mesh);
+    return b ? b->n_tris : 0;
+}
 void mrth_mesh_get_verts(mrth_scene* s, int mesh, float* out) {
-    const mrt_blas& b = s->blas.at((size_t)mesh);
+    const mrt_blas* bp = mesh_or_null(s, mesh);
+    if (!bp) return;
+    const mrt_blas& b = *bp;
     std::memcpy(out, &s->tri_verts[9 * (size_t)b.first_tri], 36 * (size_t)b.n_tris);
 }
-uint64_t mrth_mesh_node_count(mrth_scene* s, int mesh) { return s->blas.at((size_t)mesh).n_nodes; }
+uint64_t mrth_mesh_node_count(mrth_scene* s, int mesh) {
+    const mrt_blas* b = mesh_or_null(s, mesh);
+    return b ? b->n_nodes : 0;
+}
 
 int mrth_add_sphere(mrth_scene* s, int material, float cx, float cy, float cz, float radius) {
     if (!valid_material(s, material, false)) return MRT_E_INVALID;
@@ -880,7 +899,8 @@ void mrth_get_camera(mrth_scene* s, float o[19]) {
     o[18] = s->cam.lens_radius;
 }
 void mrth_get_instance(mrth_scene* s, int object, float tf[16], float inv[16], float aabb[6]) {
-    uint32_t ref = s->objects.at((size_t)object);
+    if (!object_ok(s, object)) return;
+    uint32_t ref = s->objects[(size_t)object];
     if (MRT_REF_KIND(ref) != MRT_PRIM_INSTANCE) { s->err = "object is not an Instance"; return; }
     const mrt_instance& in = s->instances[MRT_REF_INDEX(ref)];
     std::memcpy(tf, in.transform, 64);
@@ -888,7 +908,10 @@ void mrth_get_instance(mrth_scene* s, int object, float tf[16], float inv[16], f
     std::memcpy(aabb, in.bmin, 12);
     std::memcpy(aabb + 3, in.bmax, 12);
 }
-void mrth_get_object_aabb(mrth_scene* s, int object, float aabb[6]) { prim_bounds(*s, s->objects.at((size_t)object), aabb, aabb + 3); }
+void mrth_get_object_aabb(mrth_scene* s, int object, float aabb[6]) {
+    if (!object_ok(s, object)) return;
+    prim_bounds(*s, s->objects[(size_t)object], aabb, aabb + 3);
+}
 
 // Image::to_rgb_bytes(Albedo | Normal) over a FloatBuffer (main.rs:694-721, final cast :718-721), rows reversed like dump (:763-768) when flip != 0
 int mrth_float_buffer_rgb8(const float* buf, uint32_t w, uint32_t h, int mode, int flip, uint8_t* out) {
