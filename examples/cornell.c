@@ -5,7 +5,10 @@
  * (tests/test_c_host.py).
  *
  *   cc -std=c11 -I include examples/cornell.c -L mass_raytrace_b200 -lmrt_host -lmrt_cuda -lm -o cornell
- *   ./cornell mass_raytrace_b200/assets/cube.ply 512 512 64 out.png
+ *   ./cornell mass_raytrace_b200/assets/cube.ply 512 512 64 out.png [n_gpus]
+ *
+ * With n_gpus > 1 the same calls drive that many devices of this process (mrt_context_create_multi): the 64 samples are split
+ * over them, merged by one NCCL reduce, and the image is byte for byte the one a single GPU gives.
  */
 #include <math.h>
 #include <stdio.h>
@@ -33,13 +36,14 @@ static int add_cube(mrth_scene* s, int cube, float tx, float ty, float tz, float
 
 int main(int argc, char** argv) {
     if (argc < 6) {
-        fprintf(stderr, "usage: %s cube.ply width height spp out.ppm|out.png\n", argv[0]);
+        fprintf(stderr, "usage: %s cube.ply width height spp out.ppm|out.png [n_gpus]\n", argv[0]);
         return 1;
     }
     const char* ply = argv[1];
     const uint32_t w = (uint32_t)atoi(argv[2]), h = (uint32_t)atoi(argv[3]), spp = (uint32_t)atoi(argv[4]);
-    if (w == 0 || h == 0 || spp == 0) {
-        fprintf(stderr, "width, height and spp must be positive\n");
+    const int n_gpus = argc > 6 ? atoi(argv[6]) : 1;
+    if (w == 0 || h == 0 || spp == 0 || n_gpus < 1 || n_gpus > 64) {
+        fprintf(stderr, "width, height, spp and n_gpus must be positive\n");
         return 1;
     }
 
@@ -73,7 +77,13 @@ int main(int argc, char** argv) {
     mrth_camera(s, 37.0f, from, at, up, (float)w / (float)h, 0.0f, 20.0f);
 
     mrt_context* ctx = NULL;
-    if (mrt_context_create(0, NULL, &ctx) != MRT_OK) return die_ctx(NULL, "mrt_context_create");
+    if (n_gpus == 1) {
+        if (mrt_context_create(0, NULL, &ctx) != MRT_OK) return die_ctx(NULL, "mrt_context_create");
+    } else { /* the render-thread fan-out of main.rs:159-170, as devices */
+        int devices[64];
+        for (int i = 0; i < n_gpus; ++i) devices[i] = i;
+        if (mrt_context_create_multi(devices, n_gpus, &ctx) != MRT_OK) return die_ctx(NULL, "mrt_context_create_multi");
+    }
     if (mrt_scene_upload(ctx, mrth_scene_desc(s)) != MRT_OK) return die_ctx(ctx, "mrt_scene_upload");
     if (mrt_camera_set(ctx, mrth_scene_camera(s)) != MRT_OK) return die_ctx(ctx, "mrt_camera_set");
 

@@ -217,6 +217,7 @@ typedef struct mrt_stats {
     float generate_ms;
     uint64_t scene_bytes;     /* device bytes of the uploaded scene */
     uint64_t pool_slots;      /* paths in flight (entries per ray queue) */
+    uint64_t node_bytes;      /* bytes of one inner-node record of the uploaded acceleration structure (what one node visit fetches) */
 } mrt_stats;
 
 typedef struct mrt_context mrt_context;
@@ -226,6 +227,36 @@ int mrt_context_create(int device, void* stream, mrt_context** out);
 void mrt_context_destroy(mrt_context* ctx);
 const char* mrt_last_error(mrt_context* ctx); /* ctx may be NULL: last create() error */
 int mrt_abi_version(void);
+
+
+/* ---- more than one GPU ------------------------------------------------------------------------------------------------
+ * The reference scales by letting every render thread trace WHOLE frames into a private buffer and adding them into the shared
+ * image (thread fan-out main.rs:159-170 and :235-250, Image::merge :629-638). The B200 equivalent: the samples of every pixel
+ * are split over the GPUs, each accumulates its share into its own exact (int64) image, and ONE NCCL sum-reduce over NVLink
+ * merges them onto the root. Sample s of pixel p uses the same Philox stream wherever it is rendered and the sums are integers,
+ * so the merged image is bit-identical to the one a single GPU renders.
+ *
+ * Two ways to get there, same code underneath (NCCL is loaded with dlopen("libnccl.so.2") on first use; a host that never
+ * asks for more than one GPU does not need it):
+ *   one process, several GPUs   mrt_context_create_multi(devices, n): the handle drives all n devices; every entry point below
+ *                               works on it unchanged (scene uploads are replicated device-to-device, renders are split).
+ *   one process per GPU         each rank creates its own context (mrt_context_create), rank 0 calls mrt_comm_unique_id and hands
+ *                               the 128 bytes to the others by whatever means the host has, all call mrt_comm_init_rank.
+ * In both cases mrt_render / mrt_render_accumulate become COLLECTIVE: every member is called with the SAME arguments, renders
+ * its share mrt_sample_range(rank, size, ...) of [spp_begin, spp_begin + spp_count) and the call returns after the reduce. The
+ * merged image lives on the root (rank 0 / devices[0]); the other members' images are cleared by the merge (they are the
+ * threads' private buffers of main.rs:246). Output pointers may be NULL on non-root ranks. */
+int mrt_context_create_multi(const int* devices, int n_devices, mrt_context** out);
+#define MRT_COMM_ID_BYTES 128
+int mrt_comm_unique_id(uint8_t id[MRT_COMM_ID_BYTES]);
+int mrt_comm_init_rank(mrt_context* ctx, const uint8_t id[MRT_COMM_ID_BYTES], int rank, int n_ranks);
+int mrt_comm_rank(mrt_context* ctx, int* rank, int* size); /* (0, 1) for a plain context; (0, n) for a multi-device handle */
+/* The merge on its own, for hosts that choose the sample ranges themselves (MRT_OPT_COMM_SPLIT = 0 makes
+ * mrt_render_accumulate local again): sums every member's accumulators, non-finite flags and sample count onto the root. */
+int mrt_comm_reduce(mrt_context* ctx);
+/* The split rule (pure function, no GPU): member `rank` of `size` renders [*begin, *begin + *count); contiguous, near-equal,
+ * covering [spp_begin, spp_begin + spp_count) exactly once. */
+int mrt_sample_range(int rank, int size, uint32_t spp_begin, uint32_t spp_count, uint32_t* begin, uint32_t* count);
 
 /* replaces Arc::new(world) main.rs:157 (after world.build_bvh() main.rs:112): copies the scene to the device once */
 int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* scene);
@@ -274,6 +305,8 @@ enum {
                                   no bound, or 4 when a mesh's tree is deep */
     MRT_OPT_BVH_LEAF_TRIS = 9, /* SAH rebuild at the next mrt_scene_upload: most triangles per BLAS leaf, 1..4 (default 4) */
     MRT_OPT_BVH_TRI_COST = 10, /* SAH rebuild: cost of one triangle test in hundredths of a node visit (default 100) */
+    MRT_OPT_COMM_SPLIT = 13,   /* 1 (default): on a context with a communicator mrt_render_accumulate splits the sample range and merges; 0: it renders
+                                  the range it is given, locally, and the host calls mrt_comm_reduce */
     MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 65536, 0 = off) */
 };
 int mrt_set_option(mrt_context* ctx, int option, uint64_t value);

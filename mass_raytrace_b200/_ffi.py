@@ -50,7 +50,7 @@ class mrt_stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("instance_tests", C.c_uint64), ("volume_tests", C.c_uint64), ("iterations", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_float), ("extend_ms", C.c_float), ("shade_ms", C.c_float), ("generate_ms", C.c_float),
-                ("scene_bytes", C.c_uint64), ("pool_slots", C.c_uint64)]
+                ("scene_bytes", C.c_uint64), ("pool_slots", C.c_uint64), ("node_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -60,6 +60,12 @@ class mrt_stats(C.Structure):
 CUDA_API = {
     "mrt_abi_version": (C.c_int, []),
     "mrt_context_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mrt_context_create_multi": (C.c_int, [i32p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mrt_comm_unique_id": (C.c_int, [u8p]),
+    "mrt_comm_init_rank": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int]),
+    "mrt_comm_rank": (C.c_int, [C.c_void_p, i32p, i32p]),
+    "mrt_comm_reduce": (C.c_int, [C.c_void_p]),
+    "mrt_sample_range": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, u32p, u32p]),
     "mrt_context_destroy": (None, [C.c_void_p]),
     "mrt_last_error": (C.c_char_p, [C.c_void_p]),
     "mrt_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(mrt_scene_desc)]),

@@ -522,17 +522,48 @@ class Renderer:
     """One GPU behind the C ABI of include/mrt.h. Replaces render() (main.rs:150-295); no CPU fallback."""
 
     OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_POOL_SLOTS, OPT_REFILL_LANES, OPT_FINISH_PATHS = 1, 2, 3, 4, 8
-    OPT_BVH_LEAF_TRIS, OPT_BVH_TRI_COST, OPT_DEVICE_BUILD, OPT_NODE_BURST = 9, 10, 11, 12
+    OPT_BVH_LEAF_TRIS, OPT_BVH_TRI_COST, OPT_DEVICE_BUILD, OPT_NODE_BURST, OPT_COMM_SPLIT = 9, 10, 11, 12, 13
 
     def __init__(self, device=0, stream=None):
+        """device: one CUDA device index, or a list of them -- then the handle drives all of them in this process
+        (mrt_context_create_multi: renders are split by samples and merged with one NCCL reduce)."""
         self.lib = _ffi.cuda_lib()
         h = C.c_void_p()
-        rc = self.lib.mrt_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.lib.mrt_context_create_multi(devs, len(device), C.byref(h))
+            what = f"mrt_context_create_multi({list(device)})"
+        else:
+            rc = self.lib.mrt_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+            what = f"mrt_context_create({device})"
         if rc != 0:
-            raise MrtError(f"mrt_context_create({device}) = {rc}: {self.lib.mrt_last_error(None).decode()}")
+            raise MrtError(f"{what} = {rc}: {self.lib.mrt_last_error(None).decode()}")
         self._h = h
         self.size = None
         self._scene_keepalive = None
+
+    # ---- one process per GPU: rank 0 makes the id, every rank joins (the host moves the 128 bytes however it likes) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        lib = _ffi.cuda_lib()
+        rc = lib.mrt_comm_unique_id(buf)
+        if rc != 0:
+            raise MrtError(f"mrt_comm_unique_id = {rc}: {lib.mrt_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init_rank(self, unique_id, rank, n_ranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.mrt_comm_init_rank(self._h, buf, int(rank), int(n_ranks)), "mrt_comm_init_rank")
+
+    def comm_rank(self):
+        r, n = C.c_int(0), C.c_int(1)
+        self._check(self.lib.mrt_comm_rank(self._h, C.byref(r), C.byref(n)), "mrt_comm_rank")
+        return r.value, n.value
+
+    def comm_reduce(self):
+        """Image::merge over the members (main.rs:629-638): one NCCL sum-reduce onto rank 0."""
+        self._check(self.lib.mrt_comm_reduce(self._h), "mrt_comm_reduce")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -561,7 +563,7 @@ struct mrt_context {
     // scene arrays live in a grow-only device arena (one buffer per array kind) so that re-uploading a scene of similar size
     // -- every frame of an animation, main.rs:104-117 -- costs no cudaMalloc / cudaFree; host data goes through two pinned
     // staging chunks so that the copies are real DMA and overlap the host-side memcpy into the next chunk
-    struct DevBuf { void* p = nullptr; size_t cap = 0; };
+    struct DevBuf { void* p = nullptr; size_t cap = 0; size_t used = 0; };
     std::vector<DevBuf> scene_bufs;
     size_t scene_buf_next = 0;
     void* stage[2] = {nullptr, nullptr};
@@ -599,6 +601,13 @@ struct mrt_context {
     uint32_t auto_refill_lanes = kRefillLanes, auto_node_burst = kNodeBurst;
     uint32_t opt_node_burst = 0;  // 0 = by scene
     mrt_stats stats{};
+    // more than one GPU (mrt_comm.inc): a communicator, and for a multi-device handle the contexts of the other devices
+    void* comm = nullptr;  // ncclComm_t
+    int comm_rank = 0, comm_size = 1;
+    bool comm_split = true;               // MRT_OPT_COMM_SPLIT
+    std::vector<mrt_context*> peers;      // devices[1..] of mrt_context_create_multi (owned by this, the leader)
+    unsigned long long* d_count = nullptr;  // sample-count cell of the reduce
+    unsigned long long* h_count = nullptr;  // pinned
     int grid_extend[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [count visits][0 plain, 1 volumes, 2 alpha-tested triangles (+ volumes)]
     int grid_shade = 0, grid_generate = 0;
 };
@@ -618,6 +627,8 @@ static int fail(mrt_context* ctx, int code, const std::string& msg) {
     ctx->err = msg;
     return code;
 }
+
+#include "mrt_comm.inc"
 
 constexpr size_t kStageChunk = 32u << 20;
 
@@ -666,6 +677,7 @@ static int arena_alloc(mrt_context* ctx, size_t bytes, void** out) {
     int rc = grow(ctx, buf, bytes);
     if (rc) return rc;
     ctx->scene_bytes += bytes;
+    buf.used = bytes;
     *out = buf.p;
     return MRT_OK;
 }
@@ -738,6 +750,60 @@ static void free_image(mrt_context* ctx) {
     ctx->w = ctx->h = ctx->count = 0;
 }
 
+// Multi-device handle: the scene is validated, built and uploaded ONCE (on devices[0]); the other devices receive the finished
+// device arrays over NVLink (cudaMemcpyPeerAsync, array by array of the arena) with the pointers of DScene rebased.
+static int replicate_scene(mrt_context* from, mrt_context* to) {
+    mrt_context* ctx = to;  // MRT_CUDA reports on the receiving context
+    MRT_CUDA(cudaSetDevice(to->device));
+    cudaStreamSynchronize(to->stream);
+    free_scene(to);
+    const size_t n = from->scene_buf_next;
+    std::vector<std::pair<const char*, const char*>> map(n);  // leader array -> this device's copy
+    for (size_t k = 0; k < n; ++k) {
+        const mrt_context::DevBuf& src = from->scene_bufs[k];
+        void* dst = nullptr;
+        int rc = arena_alloc(to, src.used, &dst);
+        if (rc) return rc;
+        MRT_CUDA(cudaMemcpyPeerAsync(dst, to->device, src.p, from->device, src.used, to->stream));
+        map[k] = {static_cast<const char*>(src.p), static_cast<const char*>(dst)};
+    }
+    auto rebase = [&](auto*& ptr) {
+        if (!ptr) return;
+        const char* q = reinterpret_cast<const char*>(ptr);
+        for (size_t k = 0; k < n; ++k) {
+            if (q >= map[k].first && q < map[k].first + std::max<size_t>(from->scene_bufs[k].used, 1)) {
+                ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(map[k].second + (q - map[k].first));
+                return;
+            }
+        }
+    };
+    DScene d = from->scene;
+    rebase(d.nodes); rebase(d.spheres); rebase(d.sphere_aux); rebase(d.tri_verts); rebase(d.tri_map); rebase(d.tri_shading);
+    rebase(d.instances); rebase(d.blas); rebase(d.volumes); rebase(d.materials); rebase(d.surfaces); rebase(d.textures); rebase(d.texels);
+    MRT_CUDA(cudaStreamSynchronize(to->stream));
+    to->scene = d;
+    to->has_scene = true;
+    to->auto_refill_lanes = from->auto_refill_lanes;
+    to->auto_node_burst = from->auto_node_burst;
+    to->material_kinds = from->material_kinds;
+    return MRT_OK;
+}
+
+// runs fn(member) for the leader (on the calling thread) and for each peer device (one thread each); first error wins
+template <class Fn>
+static int for_each_member(mrt_context* ctx, Fn fn) {
+    if (ctx->peers.empty()) return fn(ctx);
+    std::vector<int> rc(ctx->peers.size(), MRT_OK);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < ctx->peers.size(); ++k) th.emplace_back([&, k] { rc[k] = fn(ctx->peers[k]); });
+    int r0 = fn(ctx);
+    for (auto& t : th) t.join();
+    if (r0) return r0;
+    for (size_t k = 0; k < rc.size(); ++k)
+        if (rc[k]) { ctx->err = "device " + std::to_string(ctx->peers[k]->device) + ": " + ctx->peers[k]->err; return rc[k]; }
+    return MRT_OK;
+}
+
 extern "C" {
 
 int mrt_abi_version(void) { return MRT_ABI_VERSION; }
@@ -806,8 +872,17 @@ int mrt_context_create(int device, void* stream, mrt_context** out) {
 
 void mrt_context_destroy(mrt_context* ctx) {
     if (!ctx) return;
+    for (mrt_context* p : ctx->peers) mrt_context_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) {
+        std::string why;
+        if (NcclApi* api = nccl_api(why)) api->CommDestroy(static_cast<ncclComm_t>(ctx->comm));
+        ctx->comm = nullptr;
+    }
+    cudaFree(ctx->d_count);
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
     free_scene(ctx);
     release_scene_arena(ctx);
     free_pool(ctx);
@@ -901,7 +976,10 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if (!ctx) return MRT_E_INVALID;
     int rc = scene_upload_impl(ctx, s, ctx->opt_device_build != 0);
     if (rc == kRetryOnHost) rc = scene_upload_impl(ctx, s, false);
-    return rc;
+    if (rc) return rc;
+    for (mrt_context* p : ctx->peers)
+        if ((rc = replicate_scene(ctx, p))) return fail(ctx, rc, "device " + std::to_string(p->device) + ": " + p->err);
+    return MRT_OK;
 }
 
 static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device) {
@@ -1388,6 +1466,7 @@ int mrt_camera_set(mrt_context* ctx, const mrt_camera* c) {
     d.v = make_float3(c->v[0], c->v[1], c->v[2]);
     d.lens_radius = c->lens_radius;
     ctx->has_camera = true;
+    for (mrt_context* p : ctx->peers) { p->cam = d; p->has_camera = true; }
     return MRT_OK;
 }
 
@@ -1431,8 +1510,12 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     return MRT_OK;
 }
 
+static int accum_reset_one(mrt_context* ctx, uint32_t w, uint32_t h);
 int mrt_accum_reset(mrt_context* ctx, uint32_t w, uint32_t h) {
     if (!ctx) return MRT_E_INVALID;
+    return for_each_member(ctx, [=](mrt_context* m) { return accum_reset_one(m, w, h); });
+}
+static int accum_reset_one(mrt_context* ctx, uint32_t w, uint32_t h) {
     if (w < 2 || h < 2 || (uint64_t)w * h > 0x7FFFFFFFull) return fail(ctx, MRT_E_INVALID, "image size out of range");
     MRT_CUDA(cudaSetDevice(ctx->device));
     if (ctx->w != w || ctx->h != h || !ctx->d_accum) {
@@ -1478,7 +1561,39 @@ static int ensure_pool(mrt_context* ctx, uint64_t total_work, uint32_t regions) 
     return MRT_OK;
 }
 
+static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_count, uint32_t max_depth, uint64_t seed);
+static int comm_reduce(mrt_context* ctx);
+
+int mrt_sample_range(int rank, int size, uint32_t spp_begin, uint32_t spp_count, uint32_t* begin, uint32_t* count) {
+    if (size < 1 || rank < 0 || rank >= size || !begin || !count) return MRT_E_INVALID;
+    const uint64_t a = (uint64_t)spp_count * (uint64_t)rank / (uint64_t)size, b = (uint64_t)spp_count * (uint64_t)(rank + 1) / (uint64_t)size;
+    *begin = spp_begin + (uint32_t)a;
+    *count = (uint32_t)(b - a);
+    return MRT_OK;
+}
+
+// PASS B over the members of a communicator: each renders its share of the sample range, then the one reduce (main.rs:235-294, 629-638)
 int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_count, uint32_t max_depth, uint64_t seed) {
+    if (!ctx) return MRT_E_INVALID;
+    if (ctx->comm_size == 1 || !ctx->comm_split) return render_accumulate_local(ctx, spp_begin, spp_count, max_depth, seed);
+    if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, MRT_E_INVALID, "sample range overflows 32 bits");
+    int rc;
+    if (!ctx->peers.empty()) {  // one process, several devices: member k = k-th device
+        rc = for_each_member(ctx, [=](mrt_context* m) {
+            uint32_t b = 0, c = 0;
+            mrt_sample_range(m->comm_rank, m->comm_size, spp_begin, spp_count, &b, &c);
+            return render_accumulate_local(m, b, c, max_depth, seed);
+        });
+    } else {  // one process per GPU
+        uint32_t b = 0, c = 0;
+        mrt_sample_range(ctx->comm_rank, ctx->comm_size, spp_begin, spp_count, &b, &c);
+        rc = render_accumulate_local(ctx, b, c, max_depth, seed);
+    }
+    if (rc) return rc;
+    return comm_reduce(ctx);
+}
+
+static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_count, uint32_t max_depth, uint64_t seed) {
     int rc = check_ready(ctx);
     if (rc) return rc;
     if (!ctx->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
@@ -1492,6 +1607,7 @@ int mrt_render_accumulate(mrt_context* ctx, uint32_t spp_begin, uint32_t spp_cou
     st.iterations = st.extend_launches = st.kernel_launches = 0;
     st.render_ms = st.extend_ms = st.shade_ms = st.generate_ms = 0.0f;
     st.scene_bytes = ctx->scene_bytes;
+    st.node_bytes = sizeof(DNode);
     if (total == 0) { st.pool_slots = ctx->pool.capacity; return MRT_OK; }
     RenderParams rp{ctx->w, ctx->h, npix, spp_begin, max_depth, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), ctx->opt_refill_lanes ? ctx->opt_refill_lanes : ctx->auto_refill_lanes, ctx->opt_node_burst ? ctx->opt_node_burst : ctx->auto_node_burst, ctx->opt_finish_paths, 0u, {}};
     const uint32_t regions = shade_regions(ctx, rp.region);
@@ -1612,6 +1728,10 @@ int mrt_render(mrt_context* ctx, uint32_t w, uint32_t h, uint32_t spp_begin, uin
     if (rc) return rc;
     if ((rc = mrt_accum_reset(ctx, w, h))) return rc;
     if ((rc = mrt_render_accumulate(ctx, spp_begin, spp_count, max_depth, seed))) return rc;
+    if (ctx->comm_rank != 0 && ctx->comm_split) {  // the merged image lives on the root; this member's buffer was cleared by the merge
+        if (out_count) *out_count = 0;
+        return MRT_OK;
+    }
     return mrt_accum_download(ctx, sum_rgb, sum_bounces, out_count);
 }
 
@@ -1638,9 +1758,17 @@ int mrt_resolve_rgb8(mrt_context* ctx, int mode, int flip, uint32_t count, uint8
     return MRT_OK;
 }
 
+static int set_option_one(mrt_context* ctx, int option, uint64_t value);
 int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
     if (!ctx) return MRT_E_INVALID;
+    int rc = set_option_one(ctx, option, value);
+    for (mrt_context* p : ctx->peers)
+        if (!rc) rc = set_option_one(p, option, value);
+    return rc;
+}
+static int set_option_one(mrt_context* ctx, int option, uint64_t value) {
     switch (option) {
+        case MRT_OPT_COMM_SPLIT: ctx->comm_split = value != 0; return MRT_OK;
         case MRT_OPT_COUNT_VISITS: ctx->opt_count = value != 0; return MRT_OK;
         case MRT_OPT_TIME_KERNELS: ctx->opt_time = value != 0; return MRT_OK;
         case MRT_OPT_POOL_SLOTS:
@@ -1675,13 +1803,174 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
 int mrt_get_stats(mrt_context* ctx, mrt_stats* out) {
     if (!ctx || !out) return MRT_E_INVALID;
     *out = ctx->stats;
+    for (const mrt_context* p : ctx->peers) {  // a multi-device handle reports the whole job: counts summed, times = the slowest device
+        const mrt_stats& q = p->stats;
+        out->paths += q.paths; out->rays += q.rays; out->node_visits += q.node_visits; out->tri_tests += q.tri_tests;
+        out->sphere_tests += q.sphere_tests; out->instance_tests += q.instance_tests; out->volume_tests += q.volume_tests;
+        out->extend_launches += q.extend_launches; out->kernel_launches += q.kernel_launches;
+        out->iterations = std::max(out->iterations, q.iterations);
+        out->render_ms = std::max(out->render_ms, q.render_ms); out->extend_ms = std::max(out->extend_ms, q.extend_ms);
+        out->shade_ms = std::max(out->shade_ms, q.shade_ms); out->generate_ms = std::max(out->generate_ms, q.generate_ms);
+    }
     return MRT_OK;
 }
 
 int mrt_synchronize(mrt_context* ctx) {
     if (!ctx) return MRT_E_INVALID;
+    for (mrt_context* p : ctx->peers) {
+        cudaSetDevice(p->device);
+        MRT_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    MRT_CUDA(cudaSetDevice(ctx->device));
     MRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return MRT_OK;
+}
+
+// ---- communicators ---------------------------------------------------------------------------------------------------
+static int nccl_fail(mrt_context* ctx, NcclApi* api, const char* what, ncclResult_t r) {
+    return fail(ctx, MRT_E_CUDA, std::string(what) + ": " + (api && api->GetErrorString ? api->GetErrorString(r) : "NCCL error"));
+}
+static int comm_cells(mrt_context* ctx) {
+    if (ctx->d_count) return MRT_OK;
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    MRT_CUDA(cudaMalloc(&ctx->d_count, sizeof(unsigned long long)));
+    MRT_CUDA(cudaMallocHost(&ctx->h_count, sizeof(unsigned long long)));
+    return MRT_OK;
+}
+
+int mrt_context_create_multi(const int* devices, int n_devices, mrt_context** out) {
+    if (!out) { g_create_error = "out is NULL"; return MRT_E_INVALID; }
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > 255) { g_create_error = "device list is empty or longer than 255"; return MRT_E_INVALID; }
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) { g_create_error = "device listed twice"; return MRT_E_INVALID; }
+    mrt_context* lead = nullptr;
+    int rc = mrt_context_create(devices[0], nullptr, &lead);
+    if (rc) return rc;
+    if (n_devices == 1) { *out = lead; return MRT_OK; }
+    auto bail = [&](int code, const std::string& msg) { g_create_error = msg; mrt_context_destroy(lead); return code; };
+    for (int i = 1; i < n_devices; ++i) {
+        mrt_context* p = nullptr;
+        if ((rc = mrt_context_create(devices[i], nullptr, &p))) { mrt_context_destroy(lead); return rc; }
+        lead->peers.push_back(p);
+    }
+    std::string why;
+    NcclApi* api = nccl_api(why);
+    if (!api) return bail(MRT_E_UNSUPPORTED, why);
+    std::vector<ncclComm_t> comms((size_t)n_devices);
+    ncclResult_t r = api->CommInitAll(comms.data(), n_devices, devices);
+    if (r != ncclSuccess) return bail(MRT_E_CUDA, std::string("ncclCommInitAll: ") + api->GetErrorString(r));
+    for (int i = 0; i < n_devices; ++i) {
+        mrt_context* m = i == 0 ? lead : lead->peers[(size_t)i - 1];
+        m->comm = comms[(size_t)i];
+        m->comm_rank = i;
+        m->comm_size = n_devices;
+        if ((rc = comm_cells(m))) return bail(rc, m->err);
+        // scene replication goes device to device: direct over NVLink where peer access can be enabled, staged otherwise
+        if (i > 0) {
+            int can = 0;
+            cudaSetDevice(devices[i]);
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devices[0], 0);
+            cudaGetLastError();  // "already enabled" is fine
+        }
+    }
+    cudaSetDevice(devices[0]);
+    *out = lead;
+    return MRT_OK;
+}
+
+int mrt_comm_unique_id(uint8_t id[MRT_COMM_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) == MRT_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!id) return MRT_E_INVALID;
+    std::string why;
+    NcclApi* api = nccl_api(why);
+    if (!api) { g_create_error = why; return MRT_E_UNSUPPORTED; }
+    ncclUniqueId u;
+    ncclResult_t r = api->GetUniqueId(&u);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return MRT_E_CUDA; }
+    std::memcpy(id, u.internal, MRT_COMM_ID_BYTES);
+    return MRT_OK;
+}
+
+int mrt_comm_init_rank(mrt_context* ctx, const uint8_t id[MRT_COMM_ID_BYTES], int rank, int n_ranks) {
+    if (!ctx) return MRT_E_INVALID;
+    if (!id || n_ranks < 1 || n_ranks > 255 || rank < 0 || rank >= n_ranks) return fail(ctx, MRT_E_INVALID, "bad rank / n_ranks");
+    if (ctx->comm || !ctx->peers.empty()) return fail(ctx, MRT_E_STATE, "context already belongs to a communicator");
+    if (n_ranks == 1) return MRT_OK;
+    std::string why;
+    NcclApi* api = nccl_api(why);
+    if (!api) return fail(ctx, MRT_E_UNSUPPORTED, why);
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    std::memcpy(u.internal, id, MRT_COMM_ID_BYTES);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = api->CommInitRank(&comm, n_ranks, u, rank);
+    if (r != ncclSuccess) return nccl_fail(ctx, api, "ncclCommInitRank", r);
+    ctx->comm = comm;
+    ctx->comm_rank = rank;
+    ctx->comm_size = n_ranks;
+    return comm_cells(ctx);
+}
+
+int mrt_comm_rank(mrt_context* ctx, int* rank, int* size) {
+    if (!ctx) return MRT_E_INVALID;
+    if (rank) *rank = ctx->comm_rank;
+    if (size) *size = ctx->comm_size;
+    return MRT_OK;
+}
+
+// Image::merge (main.rs:629-638) across the members: accumulators (+ folded non-finite flags) and sample counts summed onto
+// member 0 on the render streams; the other members' images are cleared.
+static int comm_reduce(mrt_context* ctx) {
+    if (ctx->comm_size == 1) return MRT_OK;
+    std::string why;
+    NcclApi* api = nccl_api(why);
+    if (!api) return fail(ctx, MRT_E_UNSUPPORTED, why);
+    std::vector<mrt_context*> members{ctx};
+    members.insert(members.end(), ctx->peers.begin(), ctx->peers.end());
+    for (mrt_context* m : members) {
+        if (!m->d_accum) return fail(ctx, MRT_E_STATE, "no image (mrt_accum_reset)");
+        if (m->w != ctx->w || m->h != ctx->h) return fail(ctx, MRT_E_STATE, "members hold images of different sizes");
+    }
+    const uint32_t npix = ctx->w * ctx->h;
+    for (mrt_context* m : members) {
+        MRT_CUDA(cudaSetDevice(m->device));
+        k_fold_flags<<<m->n_sms * 4, 256, 0, m->stream>>>(m->d_accum, m->d_nonfinite, npix);
+        k_set_cell<<<1, 1, 0, m->stream>>>(m->d_count, (unsigned long long)m->count);
+    }
+    ncclResult_t r = api->GroupStart();
+    if (r != ncclSuccess) return nccl_fail(ctx, api, "ncclGroupStart", r);
+    for (mrt_context* m : members) {
+        ncclComm_t comm = static_cast<ncclComm_t>(m->comm);
+        if (r == ncclSuccess) r = api->Reduce(m->d_accum, m->d_accum, (size_t)npix * 4, ncclInt64, ncclSum, 0, comm, m->stream);
+        if (r == ncclSuccess) r = api->Reduce(m->d_count, m->d_count, 1, ncclUint64, ncclSum, 0, comm, m->stream);
+    }
+    ncclResult_t r2 = api->GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(ctx, api, "ncclReduce", r);
+    if (r2 != ncclSuccess) return nccl_fail(ctx, api, "ncclGroupEnd", r2);
+    for (mrt_context* m : members) {
+        MRT_CUDA(cudaSetDevice(m->device));
+        if (m->comm_rank == 0) {
+            k_unfold_flags<<<m->n_sms * 4, 256, 0, m->stream>>>(m->d_accum, m->d_nonfinite, npix);
+            MRT_CUDA(cudaMemcpyAsync(m->h_count, m->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+        } else {  // merged into the root: this member's private image starts over
+            MRT_CUDA(cudaMemsetAsync(m->d_accum, 0, (size_t)npix * 4 * sizeof(long long), m->stream));
+            MRT_CUDA(cudaMemsetAsync(m->d_nonfinite, 0, (size_t)npix * sizeof(uint32_t), m->stream));
+        }
+    }
+    for (mrt_context* m : members) {
+        MRT_CUDA(cudaSetDevice(m->device));
+        MRT_CUDA(cudaStreamSynchronize(m->stream));
+        m->count = m->comm_rank == 0 ? (uint32_t)*m->h_count : 0u;
+    }
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    return MRT_OK;
+}
+
+int mrt_comm_reduce(mrt_context* ctx) {
+    if (!ctx) return MRT_E_INVALID;
+    return comm_reduce(ctx);
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------------------------
