@@ -370,7 +370,9 @@ def main():
                       "d2h_bytes_per_step": int(npix * 16), "ms_per_step": 1e3 * e2e_s / len(e2e_t), "steps": len(e2e_t)}
 
         if detail and world_size > 1:  # weak scaling beside it: every rank renders the config's full spp, N x the samples per step
+            r.set_option(Renderer.OPT_COMM_SPLIT, 0)  # ranges chosen here, merge called explicitly (mrt_comm_reduce)
             weak_s, (wpaths, wrays, _) = timed(3, 3, split=False, first=5000)
+            r.set_option(Renderer.OPT_COMM_SPLIT, 1)
             rec["weak"] = {"value": wpaths / weak_s / 1e6, "unit": "Mpaths/s", "mrays_per_s": wrays / weak_s / 1e6, "ms_per_step": 1e3 * weak_s / 3,
                            "spp_per_gpu_per_step": spp, "steps": 3}
         return rec, world, camera, host
