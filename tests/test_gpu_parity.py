@@ -146,6 +146,54 @@ def test_aov_book2_with_uv_mesh_texture_and_volumes(renderer, keep_topology):
         assert abs(fg - fo) < 0.01 + 0.15 * fo, (vid, fg, fo)
 
 
+def test_volume_hit_probability_per_pixel(renderer):
+    """Volume::intersect draws its free-flight distance from the path's RNG (geom.rs:638), so a primary ray through a medium
+    reports the Volume with probability 1 - exp(-density * chord) and otherwise whatever lies behind. Over 64 seeds the PER-PIXEL hit
+    frequency of each medium must agree with the oracle's like two binomial samples of the same probability, and so must the
+    distribution of the reported distances."""
+    world, camera = scenes.book2_final(boxes_per_side=12, n_cluster=200)
+    renderer.set_scene(NativeScene(world, camera))
+    orc = OracleScene(world, camera)
+    w, h, n_seeds = 240, 135, 64
+    vol_ids = [i for i, ob in enumerate(world.objects) if isinstance(ob, VolumeT)]
+    assert len(vol_ids) == 2
+    fg = {v: np.zeros((h, w)) for v in vol_ids}
+    fo = {v: np.zeros((h, w)) for v in vol_ids}
+    tg, to = {v: [] for v in vol_ids}, {v: [] for v in vol_ids}
+    for seed in range(1, n_seeds + 1):
+        g = renderer.render_aov(w, h, seed=seed)
+        o = orc.render_aov(w, h, seed=1000 + seed)
+        for v in vol_ids:
+            fg[v] += g["object"] == v
+            fo[v] += o["object"] == v
+            tg[v].append(g["t"][g["object"] == v])
+            to[v].append(o["t"][o["object"] == v])
+        behind = ~np.isin(g["object"], vol_ids) & ~np.isin(o["object"], vol_ids)
+        assert np.array_equal(g["t"][behind], o["t"][behind])  # whatever is seen through the medium is the deterministic scene
+    checked = 0
+    for v in vol_ids:
+        a, b = fg[v] / n_seeds, fo[v] / n_seeds
+        p = 0.5 * (a + b)
+        assert np.array_equal(p > 0, (a > 0) | (b > 0))
+        mid = (p > 0.05) & (p < 0.95)  # pixels where both frequencies are well inside (0, 1)
+        if mid.sum() < 200:
+            # a medium this thin (or this dense) over the view: compare the frequencies summed over the image instead
+            na, nb = fg[v].sum(), fo[v].sum()
+            assert abs(na - nb) <= 5.0 * np.sqrt(na + nb + 1.0), (v, na, nb)
+            continue
+        z = (a[mid] - b[mid]) / np.sqrt(2.0 * p[mid] * (1.0 - p[mid]) / n_seeds)
+        assert np.abs(z).max() < 6.0, (v, float(np.abs(z).max()))
+        assert 0.8 < float(np.mean(z * z)) < 1.25, (v, float(np.mean(z * z)))  # two samples of the same per-pixel probability
+        assert abs(float(np.mean(z))) < 5.0 / np.sqrt(mid.sum()), (v, float(np.mean(z)))
+        x, y = np.concatenate(tg[v]).astype(np.float64), np.concatenate(to[v]).astype(np.float64)
+        se = np.sqrt(x.var() / x.size + y.var() / y.size)
+        assert abs(x.mean() - y.mean()) < 5.0 * se, (v, x.mean(), y.mean(), se)
+        qs = [0.1, 0.5, 0.9]
+        assert np.allclose(np.quantile(x, qs), np.quantile(y, qs), rtol=0.03), (v, np.quantile(x, qs), np.quantile(y, qs))
+        checked += 1
+    assert checked >= 1
+
+
 def test_aov_menger_sponge_instances(renderer):
     """scenes/menger.rs at 3 levels: 8,000 unit-cube instances of one 12-triangle BLAS under the TLAS."""
     world, camera = scenes.menger(levels=3)
@@ -224,11 +272,13 @@ def test_aov_full_size_million_triangle_mesh(renderer, tmp_mesh_dir):
 # ------------------------------------------------------------------------------------------------------------------
 # test 2: converged renders, statistical
 # ------------------------------------------------------------------------------------------------------------------
-def stat_compare(renderer, world, camera, w, h, spp, oracle_a=None, seed=2024, rmse_factor=1.15):
-    renderer.set_scene(NativeScene(world, camera))
+def stat_compare(renderer, world, camera, w, h, spp, oracle_a=None, seed=2024, rmse_factor=1.15, orc=None, upload=True):
+    if upload:
+        renderer.set_scene(NativeScene(world, camera))
     rgb, bounces, count = renderer.render(w, h, spp, 50, seed=seed)
     assert count == spp and np.isfinite(rgb).all() and (rgb >= 0).all()
-    orc = OracleScene(world, camera)
+    if orc is None:
+        orc = OracleScene(world, camera)
     if oracle_a is None:
         a_rgb, a_b, _ = orc.render(w, h, spp, 50, seed=seed)
     else:
