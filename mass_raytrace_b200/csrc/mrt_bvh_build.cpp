@@ -310,181 +310,4 @@ Tree build_sah(std::vector<Prim>& prims, int max_leaf, int sah_depth_budget, flo
     return t;
 }
 
-// ---- binary tree -> 8-wide, quantised (mrt_wide.h) ------------------------------------------------------------------------
-namespace {
-
-struct Collapser {
-    const Node* bn;
-    int max_width;
-    WideTree out;
-    std::atomic<uint32_t> node_next{1}, prim_next{0};
-    std::atomic<int> tasks{0}, depth{0};
-    int max_tasks;
-
-    static double half_area_d(const float lo[3], const float hi[3]) {
-        const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
-        if (!(dx >= 0.0) || !(dy >= 0.0) || !(dz >= 0.0)) return 0.0;
-        return dx * dy + dy * dz + dz * dx;
-    }
-
-    // grid of a node: origin = box minimum, per axis the smallest power-of-two step with 255 steps >= extent
-    static void grid_of(const float lo[3], const float hi[3], mrt::WNode& w, double step[3]) {
-        for (int a = 0; a < 3; ++a) {
-            w.p[a] = lo[a];
-            const double ext = (double)hi[a] - (double)lo[a];
-            int e = -126;  // smallest normal step; used for flat (and for degenerate) extents
-            if (std::isfinite(ext) && ext > 0.0) {
-                e = std::max(-126, std::min(127, (int)std::ceil(std::log2(ext / 255.0))));
-                while (e < 127 && std::ldexp(255.0, e) < ext) ++e;
-                while (e > -126 && std::ldexp(255.0, e - 1) >= ext) --e;
-            } else if (!(ext <= 0.0)) {
-                e = 127;  // non-finite extent: the coarsest grid (children clamp to the whole range below)
-            }
-            w.e[a] = (uint8_t)(e + 127);
-            step[a] = std::ldexp(1.0, e);
-        }
-    }
-    // child box on the grid, rounded outwards; a box the grid cannot represent exactly or that is not finite covers its whole axis
-    static void quantise(const mrt::WNode& w, const double step[3], const float lo[3], const float hi[3], int slot, mrt::WNode& dst) {
-        for (int a = 0; a < 3; ++a) {
-            const double p = w.p[a];
-            double ql = std::floor(((double)lo[a] - p) / step[a]), qh = std::ceil(((double)hi[a] - p) / step[a]);
-            if (!std::isfinite(ql) || !std::isfinite(qh)) { ql = 0.0; qh = 255.0; }
-            ql = std::min(std::max(ql, 0.0), 255.0);
-            qh = std::min(std::max(qh, 0.0), 255.0);
-            while (ql > 0.0 && p + ql * step[a] > (double)lo[a]) ql -= 1.0;
-            while (qh < 255.0 && p + qh * step[a] < (double)hi[a]) qh += 1.0;
-            dst.qlo[a][slot] = (uint8_t)ql;
-            dst.qhi[a][slot] = (uint8_t)qh;
-        }
-    }
-
-    void process(int32_t node, uint32_t wide_idx, int d) {
-        int cur = depth.load(std::memory_order_relaxed);
-        while (d > cur && !depth.compare_exchange_weak(cur, d)) {}
-        const Node& n = bn[node];
-        // ---- the children of this wide node: start from the binary node's, open the largest inner one until the node is full ----
-        int32_t ch[mrt::kWideWidth];
-        int nc = 0;
-        if (n.left < 0) {
-            ch[nc++] = node;  // a tree that is one leaf: the root node holds it as its only child
-        } else {
-            ch[nc++] = n.left;
-            if (n.right >= 0) ch[nc++] = n.right;
-            while (nc < max_width) {
-                int best = -1;
-                double best_area = -1.0;
-                for (int k = 0; k < nc; ++k) {
-                    const Node& c = bn[ch[k]];
-                    if (c.left < 0 || c.right < 0) continue;  // a leaf, or a one-child node (kept as it is)
-                    const double a = half_area_d(c.lo, c.hi);
-                    if (a > best_area) { best_area = a; best = k; }
-                }
-                if (best < 0) break;
-                const Node& c = bn[ch[best]];
-                ch[best] = c.left;
-                ch[nc++] = c.right;
-            }
-        }
-        // ---- slots: greedy assignment maximising (child centre - node centre) . (octant direction of the slot) -------------------
-        int slot_of[mrt::kWideWidth];
-        {
-            double cost[mrt::kWideWidth][mrt::kWideWidth];
-            const double cx = 0.5 * ((double)n.lo[0] + n.hi[0]), cy = 0.5 * ((double)n.lo[1] + n.hi[1]), cz = 0.5 * ((double)n.lo[2] + n.hi[2]);
-            for (int k = 0; k < nc; ++k) {
-                const Node& c = bn[ch[k]];
-                double dx = 0.5 * ((double)c.lo[0] + c.hi[0]) - cx, dy = 0.5 * ((double)c.lo[1] + c.hi[1]) - cy, dz = 0.5 * ((double)c.lo[2] + c.hi[2]) - cz;
-                if (!std::isfinite(dx)) dx = 0.0;
-                if (!std::isfinite(dy)) dy = 0.0;
-                if (!std::isfinite(dz)) dz = 0.0;
-                for (int s = 0; s < mrt::kWideWidth; ++s) cost[k][s] = ((s & 4) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 1) ? dz : -dz);
-            }
-            bool child_done[mrt::kWideWidth] = {}, slot_used[mrt::kWideWidth] = {};
-            for (int round = 0; round < nc; ++round) {
-                int bk = -1, bs = -1;
-                double bc = -std::numeric_limits<double>::infinity();
-                for (int k = 0; k < nc; ++k) {
-                    if (child_done[k]) continue;
-                    for (int s = 0; s < mrt::kWideWidth; ++s)
-                        if (!slot_used[s] && (bk < 0 || cost[k][s] > bc)) { bc = cost[k][s]; bk = k; bs = s; }
-                }
-                child_done[bk] = true;
-                slot_used[bs] = true;
-                slot_of[bk] = bs;
-            }
-        }
-        int child_in_slot[mrt::kWideWidth];
-        for (int s = 0; s < mrt::kWideWidth; ++s) child_in_slot[s] = -1;
-        for (int k = 0; k < nc; ++k) child_in_slot[slot_of[k]] = k;
-        // ---- the node record -------------------------------------------------------------------------------------------
-        mrt::WNode w;
-        std::memset(&w, 0, sizeof w);
-        double step[3];
-        grid_of(n.lo, n.hi, w, step);
-        uint32_t n_inner = 0, n_prims = 0;
-        for (int k = 0; k < nc; ++k) {
-            const Node& c = bn[ch[k]];
-            if (c.left < 0) n_prims += c.count; else ++n_inner;
-        }
-        const uint32_t child_base = n_inner ? node_next.fetch_add(n_inner) : 0u;
-        const uint32_t prim_base = n_prims ? prim_next.fetch_add(n_prims) : 0u;
-        w.child_base = child_base;
-        w.prim_base = prim_base;
-        uint32_t rank = 0, offset = 0;
-        struct Todo { int32_t node; uint32_t wide; };
-        Todo todo[mrt::kWideWidth];
-        int n_todo = 0;
-        for (int s = 0; s < mrt::kWideWidth; ++s) {
-            const int k = child_in_slot[s];
-            if (k < 0) {  // empty slot: no bits, and a box nothing can hit
-                for (int a = 0; a < 3; ++a) { w.qlo[a][s] = 255; w.qhi[a][s] = 0; }
-                continue;
-            }
-            const Node& c = bn[ch[k]];
-            quantise(w, step, c.lo, c.hi, s, w);
-            if (c.left < 0) {
-                w.meta[s] = (uint8_t)((((1u << c.count) - 1u) << 5) | offset);
-                for (uint32_t i = 0; i < c.count; ++i) out.prim_order[prim_base + offset + i] = c.first + i;
-                offset += c.count;
-            } else {
-                w.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
-                w.imask |= (uint8_t)(1u << s);
-                todo[n_todo++] = Todo{ch[k], child_base + rank};
-                ++rank;
-            }
-        }
-        out.nodes[wide_idx] = w;
-        // ---- children: the upper levels fan out over the host's cores --------------------------------------------------------
-        std::vector<std::future<void>> futs;
-        for (int k = 0; k < n_todo; ++k) {
-            if (d <= 3 && k + 1 < n_todo && tasks.load(std::memory_order_relaxed) < max_tasks) {
-                tasks.fetch_add(1);
-                const Todo t = todo[k];
-                futs.push_back(std::async(std::launch::async, [this, t, d] { process(t.node, t.wide, d + 1); tasks.fetch_sub(1); }));
-            } else {
-                process(todo[k].node, todo[k].wide, d + 1);
-            }
-        }
-        for (auto& f : futs) f.get();
-    }
-};
-
-}  // namespace
-
-WideTree collapse_wide(const Node* bn, int32_t root, size_t n_prims, int max_width) {
-    Collapser c;
-    c.bn = bn;
-    c.max_width = std::max(2, std::min(max_width, mrt::kWideWidth));
-    c.max_tasks = (int)std::max(1u, std::thread::hardware_concurrency());
-    if (root < 0) return std::move(c.out);
-    // a wide node absorbs at least one binary inner node, so there are at most as many as binary inner nodes (n_prims - 1), and
-    // at least one; one-child chains (keep mode) can add up to one more per primitive
-    c.out.nodes.resize(std::max<size_t>(2 * n_prims + 2, 2));
-    c.out.prim_order.resize(n_prims);
-    c.process(root, 0, 1);
-    c.out.nodes.resize(c.node_next.load());
-    c.out.depth = c.depth.load();
-    return std::move(c.out);
-}
-
 }  // namespace mrt_build

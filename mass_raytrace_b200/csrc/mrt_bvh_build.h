@@ -10,8 +10,6 @@
 #include <memory>
 #include <vector>
 
-#include "mrt_wide.h"
-
 namespace mrt_build {
 
 struct alignas(16) Prim {  // two 16-byte halves: (lo, ref) and (hi, pad), loaded as one SSE register each
@@ -36,18 +34,5 @@ struct Tree {
 // Builds over prims (reordered in place so that every leaf is a contiguous range). cost_prim = cost of testing one primitive
 // relative to one node visit.
 Tree build_sah(std::vector<Prim>& prims, int max_leaf, int sah_depth_budget, float cost_prim);
-
-// The tree the kernels traverse (mrt_wide.h): a binary tree collapsed into nodes of up to `max_width` children -- a child is
-// either an inner node or a leaf of at most mrt::kWideLeafPrims primitives -- with the children placed in octant-order slots and
-// their boxes quantised onto the parent's grid. max_width = 8 is the product setting; 2 keeps a caller's binary topology as it
-// is (MRT_SCENE_KEEP_TOPOLOGY), one wide node per binary node.
-struct WideTree {
-    std::vector<mrt::WNode> nodes;     // nodes[0] = root; the inner children of a node are consecutive
-    std::vector<uint32_t> prim_order;  // position in the wide tree's primitive order -> index into the binary tree's (leaf-ordered) primitive array
-    int depth = 0;                     // wide nodes on the longest root-to-leaf path
-};
-// `bn` / `root`: a binary tree whose leaves hold first / count <= mrt::kWideLeafPrims; an inner node may lack a right child
-// (right < 0 with left >= 0: BvhNode::new over a single item, geom.rs:120-121).
-WideTree collapse_wide(const Node* bn, int32_t root, size_t n_prims, int max_width);
 
 }  // namespace mrt_build

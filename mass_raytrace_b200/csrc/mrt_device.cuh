@@ -205,8 +205,8 @@ __device__ __forceinline__ bool triangle_test(const DTriVerts& tv, const Ray& r,
 // this ray's direction sign uses ood - e, the far one ood + e, with e = 2^-21 * |o * id| -- and the |t| part by widening the final
 // interval by 2^-21 relatively. So the test never rejects a box the reference's test accepts, and nothing computed here reaches
 // a hit record. (A single slack for all axes would be wrong in practice: a ray almost parallel to an axis has |o * id| ~ 1e30
-// on that axis, and adding that to the other axes' intervals switches culling off for the whole ray.) For d == 0: b * inf - o * inf
-// is +-inf like the reference's x / 0, or NaN, and then the axis is ignored, which only accepts more.
+// on that axis, and adding that to the other axes' intervals switches culling off for the whole ray.) A ray with d == 0 on an axis
+// ignores that axis (slab_axis below), which only accepts more.
 struct SlabRay {
     V3 id;      // ~ 1 / direction
     V3 ood_lo;  // -(origin * id) -+ e: added to box.min * id
@@ -272,11 +272,20 @@ __device__ __forceinline__ float rcp_fast(float x) {
 __device__ __forceinline__ void slab_axis(float o, float d, float& id, float& ood_lo, float& ood_hi) {
     id = rcp_fast(d);
     const float p = o * id;
-    // inf and NaN products (d == 0) carry no rounding error: no slack (and no NaN from inf * 2^-21 - inf)
-    const float e = (fabsf(p) < 3.0e38f) ? fabsf(p) * 4.76837158203125e-7f : 0.0f;
+    const float e = fabsf(p) * 4.76837158203125e-7f;
     const float se = copysignf(e, id);  // d > 0: box.min is the near plane and gets -e
     ood_lo = -p - se;
     ood_hi = -p + se;
+    // d == 0 (id = +-inf), or d so small that o / d overflows: b * id + ood cannot express the reference's (b - o) / d = +-inf any
+    // more -- b * inf - o * inf is NaN whenever b and o have the same sign, and a dropped NaN next to a -inf made the far plane
+    // -inf, so that a ray exactly parallel to an axis missed every box straddling 0 on it (found by the per-pixel volume test: the
+    // centre row of an image whose camera looks along an axis). Such a ray ignores the axis instead: near -inf, far +inf for every
+    // finite plane, which only accepts more (the reference rejects when the origin lies outside the slab).
+    if (!(fabsf(p) < 3.0e38f) || !(fabsf(id) < 3.0e38f)) {
+        id = 1.17549435e-38f;
+        ood_lo = -__int_as_float(0x7f800000);
+        ood_hi = __int_as_float(0x7f800000);
+    }
 }
 __device__ __forceinline__ SlabRay slab_ray(const Ray& r) {
     SlabRay s;

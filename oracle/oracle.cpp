@@ -1673,10 +1673,55 @@ void orc_render_aov(orc_scene* s, uint32_t w, uint32_t h, uint64_t seed, int thr
 
 void orc_render(orc_scene* s, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth, uint64_t seed, int threads, float* sum_rgb,
                 uint32_t* sum_bounces, orc_counters* counters) {
-    int T = resolve_threads(threads);
+    const bool by_rows = threads < 0;  // harness addition, see below
+    int T = resolve_threads(by_rows ? 0 : threads);
     size_t npx = (size_t)w * h;
     for (size_t i = 0; i < npx * 3; ++i) sum_rgb[i] = 0.0f;  // image.clear() main.rs:233
     for (size_t i = 0; i < npx; ++i) sum_bounces[i] = 0;
+    if (by_rows) {
+        // threads < 0: the same frames, distributed over the host's cores by IMAGE ROW instead of by frame, so that a render of a
+        // few samples per pixel at a large resolution (the full-size parity tests) uses every core. Each (frame, row) has its own
+        // generator stream and each pixel still receives its frames in frame order: the output does not depend on the thread count.
+        std::atomic<uint32_t> next_row{0};
+        std::mutex mu;
+        orc_counters total{};
+        std::vector<std::thread> pool;
+        for (int i = 0; i < T; ++i) {
+            pool.emplace_back([&]() {
+                orc_counters cnt{};
+                tl_cnt = &cnt;
+                for (;;) {
+                    uint32_t y = next_row.fetch_add(1);
+                    if (y >= h) break;
+                    for (uint32_t frame = 0; frame < spp; ++frame) {
+                        Rng rng(splitmix(splitmix(splitmix(seed) + frame) ^ (0xD1B54A32D192ED03ULL * (uint64_t)(y + 1))));
+                        tl_rng = &rng;
+                        for (uint32_t x = 0; x < w; ++x) {
+                            F u = ((F)x + frand()) / (F)(w - 1);  // main.rs:258-259
+                            F v = ((F)y + frand()) / (F)(h - 1);
+                            Ray ray = s->camera.ray(u, v);
+                            V3 color;
+                            uint32_t depth = 0;
+                            trace(s->world, ray, max_depth, color, depth);
+                            size_t p = (size_t)y * w + x;
+                            sum_rgb[3 * p] += color.x;  // buffer.set + merge (main.rs:263, :629-638) for this pixel
+                            sum_rgb[3 * p + 1] += color.y;
+                            sum_rgb[3 * p + 2] += color.z;
+                            sum_bounces[p] += max_depth - depth;
+                            cnt.paths++;
+                        }
+                    }
+                }
+                tl_cnt = nullptr;
+                tl_rng = nullptr;
+                std::lock_guard<std::mutex> g(mu);
+                add_counters(total, cnt);
+            });
+        }
+        for (auto& th : pool) th.join();
+        if (counters) *counters = total;
+        return;
+    }
     std::atomic<uint32_t> next_frame{0};
     std::mutex mu;
     std::condition_variable cv;

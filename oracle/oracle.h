@@ -106,7 +106,9 @@ void orc_get_object_aabb(orc_scene*, int object, float aabb6[6]);
    (the reference Hit carries no ids); object = index in World::add order, tri = index in mesh or 0xFFFFFFFF. miss: object = 0xFFFFFFFF, t = inf. */
 void orc_render_aov(orc_scene*, uint32_t w, uint32_t h, uint64_t seed, int threads,
                     float* albedo, float* normal, uint32_t* object, uint32_t* tri, float* t, orc_counters* counters);
-/* PASS B (main.rs:233-294) bounded to `spp` merges: sum_rgb += colour, sum_bounces += MAX_DEPTH - depth. threads<=0 => max(cores-2,1). */
+/* PASS B (main.rs:233-294) bounded to `spp` merges: sum_rgb += colour, sum_bounces += MAX_DEPTH - depth. threads == 0 => max(cores-2,1)
+   threads rendering whole frames like the reference; threads < 0 => the same frames distributed over those threads by image row (harness
+   addition for few-spp renders of large images; per-(frame, row) random streams, output independent of the thread count). */
 void orc_render(orc_scene*, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth, uint64_t seed, int threads,
                 float* sum_rgb, uint32_t* sum_bounces, orc_counters* counters);
 /* Image::to_rgb_bytes(Default) + dump row flip (main.rs:640-722, 760-768): count merges -> RGB8 top row first when flip!=0 */

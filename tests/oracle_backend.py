@@ -91,8 +91,12 @@ class OracleScene(NativeScene):
         out["counters"] = cnt.as_dict()
         return out
 
-    def render(self, w, h, spp, max_depth=50, seed=1, threads=0):
+    def render(self, w, h, spp, max_depth=50, seed=1, threads=0, by_rows=False):
+        """by_rows: distribute the work over the cores by image row instead of by frame (threads < 0 in orc_render) -- for renders of
+        a few samples per pixel at a large resolution; a different (equally valid) assignment of random streams to pixels."""
         rgb, b = np.zeros((h, w, 3), np.float32), np.zeros((h, w), np.uint32)
+        if by_rows:
+            threads = -1
         cnt = orc_counters()
         self.lib.orc_render(self._h, w, h, spp, max_depth, seed, threads, fptr(rgb), b.ctypes.data_as(_ffi.u32p), C.byref(cnt))
         return rgb, b, cnt.as_dict()

@@ -131,18 +131,18 @@ def test_cfg5_ten_meshes_4k_reduced_spp(renderer, mesh10m):
 # ------------------------------------------------------------------------------------------------------------------
 def test_cfg1_book1_converged_full_config(renderer):
     world, camera = scenes.book1_spheres(1.5, aperture=0.1)
-    r = stat_compare(renderer, world, camera, 1200, 800, 10)  # the whole config: 1200x800, 10 spp
+    r = stat_compare(renderer, world, camera, 1200, 800, 10, by_rows=True)  # the whole config: 1200x800, 10 spp
     assert r["rmse_oo"] > 0
 
 
 def test_cfg2_cornell_converged_full_resolution(renderer):
     world, camera = scenes.cornell_box(1.0)
-    stat_compare(renderer, world, camera, 1024, 1024, 16)
+    stat_compare(renderer, world, camera, 1024, 1024, 16, by_rows=True)
 
 
 def test_cfg3_mesh1m_converged_full_resolution(renderer, mesh1m):
     world, camera = mesh1m
-    stat_compare(renderer, world, camera, 1920, 1080, 4)
+    stat_compare(renderer, world, camera, 1920, 1080, 4, by_rows=True)
 
 
 @pytest.fixture(scope="module")
@@ -165,7 +165,7 @@ def test_cfg4_book2_primary_rays_full_size(renderer, book2_full):
 
 def test_cfg4_book2_converged_full_resolution(renderer, book2_full):
     world, camera, orc = book2_full
-    stat_compare(renderer, world, camera, 1920, 1080, 4, orc=orc)
+    stat_compare(renderer, world, camera, 1920, 1080, 4, orc=orc, by_rows=True)
 
 
 @pytest.fixture(scope="module")
@@ -192,4 +192,4 @@ def test_cfg5_ten_meshes_primary_rays_full_size(renderer, mesh10m):
 
 def test_cfg5_ten_meshes_converged_full_resolution(renderer, mesh10m):
     world, camera, orc = mesh10m
-    stat_compare(renderer, world, camera, 3840, 2160, 2, orc=orc)
+    stat_compare(renderer, world, camera, 3840, 2160, 2, orc=orc, by_rows=True)

@@ -146,6 +146,33 @@ def test_aov_book2_with_uv_mesh_texture_and_volumes(renderer, keep_topology):
         assert abs(fg - fo) < 0.01 + 0.15 * fo, (vid, fg, fo)
 
 
+def test_aov_axis_parallel_rays(renderer):
+    """Rays with an exactly zero direction component: the centre row and centre column of an odd-sized image whose camera looks along
+    an axis. (b - o) / 0 = +-inf in the reference's slab test (geom.rs:219-220); a reciprocal-multiply form must not turn that into a
+    NaN that rejects boxes straddling the origin of that axis -- round 1 did, for every box with min < 0 < max on the axis."""
+    w = World(SkyBackground())
+    w.add(Sphere(Lambertian(SolidColor((0.5, 0.5, 0.5, 1))), V3(0, -1000, 0), 1000.0))
+    rs = np.random.RandomState(11)
+    for i in range(60):
+        c = rs.uniform(-6, 6, 3)
+        w.add(Sphere(Lambertian(SolidColor((0.2 + 0.01 * i, 0.3, 0.4, 1))), V3(c[0], abs(c[1]) * 0.5 + 0.2, c[2]), float(rs.uniform(0.2, 1.2))))
+    w.add(Sphere(Metal(0.0, SolidColor((0.9, 0.9, 0.9, 1))), V3(0, 1, 0), 1.0))  # straddles x = 0 and z = 0, centred on the view axis
+    from mass_raytrace_b200 import PlyLoader
+    cube = Model(PlyLoader.load(scenes.CUBE_PLY))
+    w.add(cube.instance(V3(0, 1, -4), V3(0, 0, 0), V3(3, 1.5, 1)))           # axis-aligned box straddling x = 0 behind the sphere
+    w.add(cube.instance(V3(-2.5, 1, 2), V3(0, 0.5, 0), V3(1, 1, 1)))
+    w.build_bvh()
+    for keep in (False, True):
+        for cam in (Camera(40.0, V3(0, 1, 12), V3(0, 1, 0), V3(0, 1, 0), 1.0, 0.0, 12.0),     # looks along -z at the height of its target: d.y == 0 on the
+                    Camera(40.0, V3(12, 1, 0), V3(0, 1, 0), V3(0, 1, 0), 1.0, 0.0, 12.0)):   # centre row, d.x (or d.z) == 0 on the centre column
+            renderer.set_scene(NativeScene(w, cam), keep_topology=keep)
+            g = renderer.render_aov(255, 255)
+            o = OracleScene(w, cam).render_aov(255, 255)
+            check_aov(g, o, albedo_exact=False)
+            assert np.array_equal(g["t"][127], o["t"][127]) and np.array_equal(g["t"][:, 127], o["t"][:, 127])
+            assert np.isfinite(g["t"][127]).mean() > 0.5
+
+
 def test_volume_hit_probability_per_pixel(renderer):
     """Volume::intersect draws its free-flight distance from the path's RNG (geom.rs:638), so a primary ray through a medium
     reports the Volume with probability 1 - exp(-density * chord) and otherwise whatever lies behind. Over 64 seeds the PER-PIXEL hit
@@ -272,7 +299,7 @@ def test_aov_full_size_million_triangle_mesh(renderer, tmp_mesh_dir):
 # ------------------------------------------------------------------------------------------------------------------
 # test 2: converged renders, statistical
 # ------------------------------------------------------------------------------------------------------------------
-def stat_compare(renderer, world, camera, w, h, spp, oracle_a=None, seed=2024, rmse_factor=1.15, orc=None, upload=True):
+def stat_compare(renderer, world, camera, w, h, spp, oracle_a=None, seed=2024, rmse_factor=1.15, orc=None, upload=True, by_rows=False):
     if upload:
         renderer.set_scene(NativeScene(world, camera))
     rgb, bounces, count = renderer.render(w, h, spp, 50, seed=seed)
@@ -280,10 +307,10 @@ def stat_compare(renderer, world, camera, w, h, spp, oracle_a=None, seed=2024, r
     if orc is None:
         orc = OracleScene(world, camera)
     if oracle_a is None:
-        a_rgb, a_b, _ = orc.render(w, h, spp, 50, seed=seed)
+        a_rgb, a_b, _ = orc.render(w, h, spp, 50, seed=seed, by_rows=by_rows)
     else:
         a_rgb, a_b = oracle_a
-    b_rgb, b_b, _ = orc.render(w, h, spp, 50, seed=seed + 1)
+    b_rgb, b_b, _ = orc.render(w, h, spp, 50, seed=seed + 1, by_rows=by_rows)
     rmse = lambda x, y: float(np.sqrt(np.mean((x.astype(np.float64) / spp - y.astype(np.float64) / spp) ** 2)))
     rmse_oo = rmse(a_rgb, b_rgb)
     rmse_go = 0.5 * (rmse(rgb, a_rgb) + rmse(rgb, b_rgb))

@@ -11,6 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         if base == "cornell": (w, c), W, H, spp = scenes.cornell_box(1.0), 1024, 1024, 16
         elif base == "menger": (w, c), W, H, spp = scenes.menger(levels=4), 1920, 1080, 8
         elif base == "book2": (w, c), W, H, spp = scenes.book2_final(), 1920, 1080, 8
+        elif base == "book1": (w, c), W, H, spp = scenes.book1_spheres(1.5, aperture=0.1), 1200, 800, 32
         elif base == "mesh10m":
             tmp = tempfile.mkdtemp(); paths, mds = [], []
             for i in range(10):
@@ -19,7 +20,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         elif base == "mesh1m":
             tmp = tempfile.mkdtemp(); n, md = scenes.write_synthetic_ply(os.path.join(tmp, "m.ply"), 1024, 512, seed=1)
             (w, c), W, H, spp = scenes.lucy_layout(os.path.join(tmp, "m.ply"), md, grid=0), 1920, 1080, 8
-        r = Renderer(0); r.set_scene(NativeScene(w, c), keep_topology=keep); r.reset(W, H); r.accumulate(0, 2)
+        r = Renderer(0)
+        if os.environ.get("MRT_AB_DEVICE_BUILD"): r.set_option(Renderer.OPT_DEVICE_BUILD, int(os.environ["MRT_AB_DEVICE_BUILD"]))
+        r.set_scene(NativeScene(w, c), keep_topology=keep); r.reset(W, H); r.accumulate(0, 2)
         best = None
         for rep in range(3):
             r.reset(W, H); r.accumulate(0, spp); st = r.stats()
