@@ -595,6 +595,7 @@ struct mrt_context {
     uint32_t opt_device_build = 1;  // MRT_OPT_DEVICE_BUILD: 0 host SAH everywhere; 1 GPU LBVH for big meshes (and for a TLAS of >= 2^20 objects);
                                     // 2 also for a TLAS of >= 16384 objects
     DevBuf build_scratch;           // raw vertices + work arrays of the GPU builder (grow-only)
+    DevBuf aov_buf;                 // output planes of mrt_render_aov (grow-only)
     int* d_depths = nullptr;        // tree depth of each GPU-built BLAS
     int* h_depths = nullptr;        // pinned
     uint32_t opt_refill_lanes = 0;  // 0 = by scene: kRefillLanesDeep under a deep BLAS, else kRefillLanes
@@ -723,6 +724,8 @@ static void release_scene_arena(mrt_context* ctx) {
     ctx->scene_bufs.clear();
     cudaFree(ctx->build_scratch.p);
     ctx->build_scratch = mrt_context::DevBuf{};
+    cudaFree(ctx->aov_buf.p);
+    ctx->aov_buf = mrt_context::DevBuf{};
     cudaFree(ctx->d_depths);
     if (ctx->h_depths) cudaFreeHost(ctx->h_depths);
     ctx->d_depths = ctx->h_depths = nullptr;
@@ -1484,15 +1487,16 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (w < 2 || h < 2 || (uint64_t)w * h > 0x7FFFFFFFull) return fail(ctx, MRT_E_INVALID, "image size out of range");
     MRT_CUDA(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)w * h;
-    float *d_alb = nullptr, *d_nrm = nullptr, *d_t = nullptr;
-    uint32_t *d_obj = nullptr, *d_tri = nullptr;
-    auto cleanup = [&]() { cudaFree(d_alb); cudaFree(d_nrm); cudaFree(d_t); cudaFree(d_obj); cudaFree(d_tri); };
-#define AOV_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MRT_E_CUDA; } } while (0)
-    if (albedo) AOV_TRY(cudaMalloc(&d_alb, npix * 12));
-    if (normal) AOV_TRY(cudaMalloc(&d_nrm, npix * 12));
-    if (t) AOV_TRY(cudaMalloc(&d_t, npix * 4));
-    if (object_id) AOV_TRY(cudaMalloc(&d_obj, npix * 4));
-    if (tri_id) AOV_TRY(cudaMalloc(&d_tri, npix * 4));
+    // the five output planes live in one grow-only buffer of the context (36 bytes per pixel): no cudaMalloc / cudaFree per call
+    int rc_buf = grow(ctx, ctx->aov_buf, npix * 36);
+    if (rc_buf) return rc_buf;
+    char* base = static_cast<char*>(ctx->aov_buf.p);
+    float* d_alb = albedo ? reinterpret_cast<float*>(base) : nullptr;
+    float* d_nrm = normal ? reinterpret_cast<float*>(base + npix * 12) : nullptr;
+    float* d_t = t ? reinterpret_cast<float*>(base + npix * 24) : nullptr;
+    uint32_t* d_obj = object_id ? reinterpret_cast<uint32_t*>(base + npix * 28) : nullptr;
+    uint32_t* d_tri = tri_id ? reinterpret_cast<uint32_t*>(base + npix * 32) : nullptr;
+#define AOV_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MRT_E_CUDA; } } while (0)
     RenderParams rp{w, h, (uint32_t)npix, 0u, 1u, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), kRefillLanes, kNodeBurst, ctx->opt_finish_paths, 0u, {}};
     const unsigned aov_grid = (unsigned)((npix + 127) / 128);
     if (ctx->scene.has_alpha) k_aov<true, true><<<aov_grid, 128, 0, ctx->stream>>>(ctx->scene, ctx->cam, rp, d_alb, d_nrm, d_obj, d_tri, d_t);
@@ -1506,7 +1510,6 @@ int mrt_render_aov(mrt_context* ctx, uint32_t w, uint32_t h, uint64_t seed, floa
     if (tri_id) AOV_TRY(cudaMemcpyAsync(tri_id, d_tri, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
     AOV_TRY(cudaStreamSynchronize(ctx->stream));
 #undef AOV_TRY
-    cleanup();
     return MRT_OK;
 }
 
@@ -1624,7 +1627,7 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
     MRT_CUDA(cudaMemcpyAsync(ctx->d_q, &ctx->h_q[2], sizeof(QueueState), cudaMemcpyHostToDevice, ctx->stream));
 
     std::vector<cudaEvent_t> tev;  // 6 events per iteration when kernel timing is on
-    const int kChunk = 8;
+    const int kChunk = 8, kDrainChunk = 3;
     int cur = 0;
     const int mode = ctx->scene.has_alpha ? 2 : (ctx->scene.n_volumes ? 1 : 0);  // which intersection code the scene needs
     // Per iteration: [finish,] generate, extend, shade (whose last block also does the bookkeeping for the next iteration). The
@@ -1632,8 +1635,8 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
     // iteration (2.5 us) ends a job as soon as few enough paths are alive, which matters for renders of a few samples per pixel.
     k_advance<<<1, 32, 0, ctx->stream>>>(ctx->d_q, pool.capacity, rp.finish_paths);
     st.kernel_launches++;
-    auto launch_chunk = [&](int slot) -> int {
-        for (int it = 0; it < kChunk; ++it) {
+    auto launch_chunk = [&](int slot, int len) -> int {
+        for (int it = 0; it < len; ++it) {
             cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             if (ctx->opt_time)
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
@@ -1668,12 +1671,17 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
         MRT_CUDA(cudaEventRecord(ctx->ev_status[slot], ctx->stream));
         return MRT_OK;
     };
-    // keep one chunk of iterations queued ahead of the one whose status is being read, so the stream never idles
-    if ((rc = launch_chunk(0))) return rc;
+    // keep one chunk of iterations queued ahead of the one whose status is being read, so the stream never idles. Once a status
+    // shows that every sample has been handed out (the job is draining), the chunks shrink: iterations queued past `done` are
+    // empty launches (~17 us each), and a short job or one GPU's share of a split job should not pay 16 of them.
+    int len = kChunk;
+    if ((rc = launch_chunk(0, len))) return rc;
     for (int c = 0;; ++c) {
-        if ((rc = launch_chunk((c + 1) & 1))) return rc;
+        if ((rc = launch_chunk((c + 1) & 1, len))) return rc;
         MRT_CUDA(cudaEventSynchronize(ctx->ev_status[c & 1]));
-        if (ctx->h_q[c & 1].done) break;
+        const QueueState& seen = ctx->h_q[c & 1];
+        if (seen.done) break;
+        if (seen.next_work == seen.total_work) len = kDrainChunk;
     }
     MRT_CUDA(cudaMemcpyAsync(&ctx->h_q[2], ctx->d_q, sizeof(QueueState), cudaMemcpyDeviceToHost, ctx->stream));
     MRT_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
