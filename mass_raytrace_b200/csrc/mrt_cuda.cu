@@ -152,15 +152,19 @@ __device__ __forceinline__ Ray camera_ray(const DCamera& cam, const RenderParams
     return r;
 }
 
+// Work item k of a job is pixel k mod w*h, sample spp_begin + k div w*h. The 64-bit division is done once per thread (for the first
+// item of this launch); every item of the launch is then a 32-bit offset from it.
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp, Pool pool,
                                                   QueueState* q, int cur) {
     const uint32_t n_new = q->n_new, n_cont = q->n_cont;
     const unsigned long long base = q->gen_base;
+    const uint32_t pixel0 = (uint32_t)(base % rp.npix), sample0 = rp.spp_begin + (uint32_t)(base / rp.npix);
     RayRec* __restrict__ out = pool.q_ext[cur] + n_cont;  // new paths follow the continuing ones: whole warps of neighbouring pixels
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-        unsigned long long wk = base + i;
-        uint32_t pixel = (uint32_t)(wk % rp.npix);
-        uint32_t sample = rp.spp_begin + (uint32_t)(wk / rp.npix);
+        const uint32_t p = pixel0 + i;  // < 2^31 + 2^26
+        const uint32_t wrap = p / rp.npix;
+        const uint32_t pixel = p - wrap * rp.npix;
+        const uint32_t sample = sample0 + wrap;
         Ray r = camera_ray(cam, rp, pixel, sample, true);
         out[i].o = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
         out[i].d = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(sample));

@@ -125,7 +125,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
-__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-8f; }  // [0,1), 24 bits
+// (0, 1), 23 bits like the reference's f32 generator (fastrand: 23 mantissa bits), but never 0: the closed-form ball sampler would
+// turn a 0 into a zero-length direction, and log(0) into an infinite free-flight distance
+__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-7f; }
 struct Rand4 {
     float x, y, z, w;
 };
@@ -342,6 +344,11 @@ __device__ __forceinline__ void trav_begin(const DScene& sc, Traversal& T, W& ws
     T.cur_inst = kNone;
     T.ref = sc.root;  // kNone for an empty world
     T.inst_base = 0;
+    // A ray whose direction has no length or is not finite misses everything. (In the reference NaN compares false everywhere: such a
+    // ray passes every box test and "hits" the first sphere it meets at t = NaN, whichever that is in its tree, and keeps bouncing
+    // as a NaN ray until the depth limit. Here it would walk the whole scene once per bounce -- measured: one such path, 0.47 s.)
+    const float len2 = length_squared(world.d);
+    if (!(len2 > 0.0f) || !(len2 < __int_as_float(0x7f800000))) T.ref = kNone;
 }
 
 // false when the traversal is complete (T.best is final). Entries pushed before an instance was entered sit below

@@ -15,7 +15,7 @@
 //   cub radix sort  (key, index) pairs  -- library code: a sort is plumbing here, not the hot path
 //   k_lbvh_tree     one thread per inner node: its key range and split from longest-common-prefix searches
 //   k_lbvh_refit    one thread per triangle, bottom-up: inner-node boxes and subtree depth (second arrival proceeds)
-//   cub scan        numbers the inner nodes that survive: subtrees of <= 4 triangles collapse into multi-triangle leaves
+//   cub scan        numbers the inner nodes that survive: subtrees of <= 2 triangles (kMaxLeaf) collapse into multi-triangle leaves
 //   k_lbvh_emit     64-byte DNodes (both child boxes + refs) at their final positions
 //   k_lbvh_gather   triangle vertices in leaf order (+ alpha flag), device-order -> caller-order map
 #pragma once
@@ -26,7 +26,10 @@
 namespace mrt {
 namespace lbvh {
 
-constexpr uint32_t kMaxLeaf = 4;
+#ifndef MRT_LBVH_MAX_LEAF
+#define MRT_LBVH_MAX_LEAF 2
+#endif
+constexpr uint32_t kMaxLeaf = MRT_LBVH_MAX_LEAF;  // triangles per leaf of a GPU-built BLAS (1 / 2 / 3 / 4 measured on the mesh workloads: 2 is 6 % faster than 4, profiles/README.md)
 
 struct Scratch {  // device arrays of one build, n = triangles, m = n - 1 inner nodes
     float4 *box_lo, *box_hi;          // [n] per triangle, caller order
