@@ -28,7 +28,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic bytes of k_extend per unit of work: one wide-node visit fetches the node record, a
+# Algorithmic bytes of k_extend per unit of work: one node visit fetches the 64-byte node record, a
 # triangle test its 3 vertices (36 B of payload), a sphere test 16 B, an instance entry the inverse matrix + meta (64 B); per
 # ray the 48-byte ray record is read and the 64-byte shade-queue entry (ray record + hit) written.
 B_TRI, B_SPHERE, B_INSTANCE, B_QUEUE_EXTEND = 36, 16, 64, 112

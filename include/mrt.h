@@ -94,7 +94,8 @@ typedef struct mrt_instance {
 
 /* Volume {neg_inv_density, target, material: Isotrophic}  geom.rs:587-591 */
 typedef struct mrt_volume {
-    uint32_t target;         /* prim ref; this build supports MRT_PRIM_SPHERE targets */
+    uint32_t target;         /* prim ref of the Intersect the medium fills: a SPHERE, or an INSTANCE entry (Model or Instance; one that is not itself
+                                in the world list carries object_id MRT_REF_NONE) */
     float neg_inv_density;
     int32_t material;        /* an MRT_MAT_ISOTROPIC entry */
     uint32_t object_id;
@@ -110,7 +111,11 @@ enum {
     MRT_MAT_SPECULAR = 5,     /* surface, p[0] = refraction_index :331 */
     MRT_MAT_MIX = 6,          /* left, right, p[0] = ratio :391 */
     MRT_MAT_ISOTROPIC = 7,    /* p[0..3] = albedo      :428 */
-    MRT_MAT_KINDS = 8
+    MRT_MAT_EVE = 8,          /* EveMaterial eve.rs:23-133, the implementer of Material::normal (tangent-space normals, geom.rs:551-560):
+                                 surface = normal + occlusion texture surface, left = albedo + roughness, right = paint / material / dirt / glow
+                                 (three MRT_SURF_TEXTURE surfaces); the bits of p[0] = index of the first of FOUR consecutive MRT_SURF_SOLID
+                                 surfaces holding the palette: color[0..2] = EveMaterialColor.colors[i], color[3] = glow[i] (i < 3) */
+    MRT_MAT_KINDS = 9
 };
 typedef struct mrt_material {
     int32_t kind;

@@ -46,6 +46,8 @@ int mrth_mat_dielectric(mrth_scene*, float ior);
 int mrth_mat_specular(mrth_scene*, float ior, int surface);
 int mrth_mat_mix(mrth_scene*, float ratio, int left, int right);
 int mrth_mat_isotropic(mrth_scene*, float r, float g, float b);
+/* EveMaterial::new (eve.rs:43-64) over three texture surfaces + EveMaterialColor {colors[4], glow} (:135-141): the implementer of Material::normal */
+int mrth_mat_eve(mrth_scene*, int normal_occlusion, int albedo_roughness, int pmdg, const float colors12[12], const float glow3[3]);
 
 void mrth_background_solid(mrth_scene*, float r, float g, float b);
 void mrth_background_sky(mrth_scene*);
@@ -74,6 +76,9 @@ int mrth_add_sphere(mrth_scene*, int material, float cx, float cy, float cz, flo
 int mrth_add_model(mrth_scene*, int mesh, int override_material);
 int mrth_add_instance(mrth_scene*, int mesh, const float t[3], const float r[3], const float s[3], int override_material);
 int mrth_add_volume_sphere(mrth_scene*, float cx, float cy, float cz, float radius, float density, float r, float g, float b);
+/* Volume::new over a Model / an Instance of a mesh (geom.rs:595-609 is generic over Intersect): the medium fills the mesh */
+int mrth_add_volume_model(mrth_scene*, int mesh, float density, float r, float g, float b);
+int mrth_add_volume_instance(mrth_scene*, int mesh, const float translation[3], const float rotation[3], const float scale[3], float density, float r, float g, float b);
 void mrth_build_bvh(mrth_scene*);
 uint64_t mrth_tlas_node_count(mrth_scene*);
 void mrth_camera(mrth_scene*, float vfov, const float from[3], const float at[3], const float up[3], float aspect, float aperture, float focus);

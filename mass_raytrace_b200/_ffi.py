@@ -110,6 +110,7 @@ def scene_api(prefix, with_desc):
         f"{p}_mat_specular": (C.c_int, [C.c_void_p, C.c_float, C.c_int]),
         f"{p}_mat_mix": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_int]),
         f"{p}_mat_isotropic": (C.c_int, [C.c_void_p] + [C.c_float] * 3),
+        f"{p}_mat_eve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float * 12), C.POINTER(C.c_float * 3)]),
         f"{p}_background_solid": (None, [C.c_void_p] + [C.c_float] * 3),
         f"{p}_background_sky": (None, [C.c_void_p]),
         f"{p}_background_skysphere": (None, [C.c_void_p, C.c_int]),
@@ -129,6 +130,8 @@ def scene_api(prefix, with_desc):
         f"{p}_add_model": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
         f"{p}_add_instance": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(f3), C.POINTER(f3), C.POINTER(f3), C.c_int]),
         f"{p}_add_volume_sphere": (C.c_int, [C.c_void_p] + [C.c_float] * 8),
+        f"{p}_add_volume_model": (C.c_int, [C.c_void_p, C.c_int] + [C.c_float] * 4),
+        f"{p}_add_volume_instance": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(f3), C.POINTER(f3), C.POINTER(f3)] + [C.c_float] * 4),
         f"{p}_build_bvh": (None, [C.c_void_p]),
         f"{p}_tlas_node_count": (C.c_uint64, [C.c_void_p]),
         f"{p}_camera": (None, [C.c_void_p, C.c_float, C.POINTER(f3), C.POINTER(f3), C.POINTER(f3), C.c_float, C.c_float, C.c_float]),

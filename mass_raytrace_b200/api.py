@@ -137,6 +137,15 @@ class Mix:  # :391
 ABSORB = ()  # impl Material for ()  material.rs:385
 
 
+@dataclass(eq=False)
+class EveMaterial:  # EveMaterial::new(no, ar, pmdg, colors) eve.rs:43-64 -- the one implementer of Material::normal (geom.rs:551-560)
+    normal_occlusion: object   # Texture surfaces (the reference loads them with WrapMode::Repeat)
+    albedo_roughness: object
+    pmdg: object               # paint, material, dirt, glow masks
+    colors: Sequence[Tuple[float, float, float]] = ((0.02, 0.02, 0.02), (0.1, 0.1, 0.1), (0.03, 0.05, 0.1), (0.08, 0.08, 0.08))  # EveMaterialColor::caldari :160
+    glow: Tuple[float, float, float] = (0.5, 0.85, 2.0)
+
+
 # ---- backgrounds (material.rs:39-190) ----------------------------------------------------------------------
 @dataclass(eq=False)
 class SolidBackground:
@@ -252,8 +261,8 @@ class Model:  # geom.rs:275
 
 
 @dataclass(eq=False)
-class Volume:  # Volume::new(target, density, albedo) geom.rs:603; target must be a Sphere
-    target: Sphere
+class Volume:  # Volume::new(target, density, albedo) geom.rs:603; target: a Sphere, a Model or an Instance (the medium fills it)
+    target: object
     density: float
     albedo: Tuple[float, float, float]
 
@@ -387,6 +396,10 @@ class NativeScene:
             h = self._fn("mat_specular")(self._h, float(m.refraction_index), self._surface(m.surface))
         elif isinstance(m, Mix):
             h = self._fn("mat_mix")(self._h, float(m.ratio), self._material(m.left), self._material(m.right))
+        elif isinstance(m, EveMaterial):
+            colors = (C.c_float * 12)(*[float(x) for c in m.colors for x in c])
+            glow = (C.c_float * 3)(*[float(x) for x in m.glow])
+            h = self._fn("mat_eve")(self._h, self._surface(m.normal_occlusion), self._surface(m.albedo_roughness), self._surface(m.pmdg), C.byref(colors), C.byref(glow))
         else:
             raise TypeError(f"unsupported material {type(m).__name__}")
         self._mat[key] = self._check(h, "material")
@@ -456,9 +469,16 @@ class NativeScene:
             h = self._fn("add_instance")(self._h, self.mesh(obj.model.triangles), _f3(obj.translation), _f3(obj.rotation), _f3(obj.scale),
                                          self._material(obj.material))
         elif isinstance(obj, Volume):
-            c = obj.target.center
-            h = self._fn("add_volume_sphere")(self._h, float(c[0]), float(c[1]), float(c[2]), float(obj.target.radius), float(obj.density),
-                                              *[float(x) for x in obj.albedo])
+            tg, alb = obj.target, [float(x) for x in obj.albedo]
+            if isinstance(tg, Sphere):
+                c = tg.center
+                h = self._fn("add_volume_sphere")(self._h, float(c[0]), float(c[1]), float(c[2]), float(tg.radius), float(obj.density), *alb)
+            elif isinstance(tg, Model):
+                h = self._fn("add_volume_model")(self._h, self.mesh(tg.triangles), float(obj.density), *alb)
+            elif isinstance(tg, Instance):
+                h = self._fn("add_volume_instance")(self._h, self.mesh(tg.model.triangles), _f3(tg.translation), _f3(tg.rotation), _f3(tg.scale), float(obj.density), *alb)
+            else:
+                raise TypeError(f"Volume over {type(tg).__name__}")
         else:
             raise TypeError(type(obj).__name__)
         return self._check(h, "World::add")

@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
     uint32_t refill_lanes = rp.refill_lanes;
     const uint32_t node_burst = rp.node_burst;
     VisitCounters cnt{0, 0, 0, 0, 0};
+    unsigned long long ray_start = 0;  // (COUNT) node visits when the lane's current ray began
+    (void)ray_start;
     uint32_t stack[kStackSize];
     Traversal T;
     T.sp = 0;
@@ -229,6 +231,12 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
             HitRec h = T.best;
             int32_t m = -1;
             if (pending) {
+#ifdef MRT_TRACE_MONSTERS
+                if (COUNT && cnt.node_visits - ray_start > 100000ull)
+                    printf("monster ray: %llu node visits, pixel %u sample %u bounce %u o (%.9g %.9g %.9g) d (%.9g %.9g %.9g) hit t %.9g prim %08x\n", cnt.node_visits - ray_start,
+                           __float_as_uint(mine[6 * kExtendThreads]), __float_as_uint(mine[7 * kExtendThreads]), __float_as_uint(mine[11 * kExtendThreads]), mine[0],
+                           mine[kExtendThreads], mine[2 * kExtendThreads], mine[3 * kExtendThreads], mine[4 * kExtendThreads], mine[5 * kExtendThreads], h.t, h.prim);
+#endif
                 if (h.prim == kNone) h.t = inf;
                 kind = Q_MISS;
                 if (h.prim != kNone) {
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
                     mine[11 * kExtendThreads] = thr.w;
                     trav_begin(sc, T, ws, Ray{V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z}}, inf);  // world.rs:68: [0.001, +inf); stores the ray in s_path 0-5
                     active = true;
+                    if (COUNT) ray_start = cnt.node_visits;
                 }
                 drained = base + want >= n;
             }
@@ -307,6 +316,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
 
 // One queue entry of Camera::trace's hit/miss handling (world.rs:69-77) in iterative form:
 // radiance += throughput * emitted; throughput *= attenuation. On return with cont == true, `e.ray` is the scattered ray.
+template <bool FULL>
 __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams& rp, long long* accum, uint32_t* nonfinite, uint32_t kind, HitEntry& e,
                                             bool& cont) {
     const float4 o = e.ray.o, d = e.ray.d, th = e.ray.thr;
@@ -327,10 +337,11 @@ __device__ __forceinline__ void shade_entry(const DScene& sc, const RenderParams
             emat = pick_material(sc, (int32_t)hr.w, key, kStreamEmit);
             mat = pick_material(sc, (int32_t)hr.w, key, kStreamMix);
         }
-        Surfel s = resolve_hit(sc, ray, h, (int32_t)hr.w);
+        Surfel s = resolve_hit<FULL>(sc, ray, h, (int32_t)hr.w);
         if (emat.kind == MRT_MAT_DIFFUSE_LIGHT) accumulate(accum, nonfinite, pixel, thr * V3{emat.p[0], emat.p[1], emat.p[2]});  // world.rs:69
+        else if (FULL && emat.kind == MRT_MAT_EVE && s.has_uv) accumulate(accum, nonfinite, pixel, thr * eve_emission(sc, emat, s.u, s.v));  // eve.rs:121-128
         ScatterOut sco;
-        scatter_kind(sc, mat, ray, s, draw4(key, kStreamScatter), sco);
+        scatter_kind<FULL>(sc, mat, ray, s, draw4(key, kStreamScatter), sco);
         if (sco.scattered) {
             thr = thr * sco.attenuation;
             bounce += 1;
@@ -357,6 +368,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // Each warp takes 32 consecutive entries of one material queue at a time (so a warp shades one material kind), streams them in
 // with coalesced 128-bit loads -- the entries of its next turn are prefetched into L2 meanwhile -- and appends the scattered
 // rays of the surviving paths to the next extend queue with one atomic per warp.
+template <bool FULL>
 __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, Pool pool,
                                                                             QueueState* q, int cur, long long* accum, uint32_t* nonfinite,
                                                                             uint32_t next_finish_paths) {
@@ -384,7 +396,7 @@ __global__ void __launch_bounds__(MRT_SHADE_THREADS, MRT_SHADE_MINB) k_shade(con
                 e.ray.d = queue[i].ray.d;
                 e.ray.thr = queue[i].ray.thr;
                 e.hit = queue[i].hit;
-                shade_entry(sc, rp, accum, nonfinite, kind, e, cont);
+                shade_entry<FULL>(sc, rp, accum, nonfinite, kind, e, cont);
             }
             const uint32_t mc = __ballot_sync(0xffffffffu, cont);
             if (mc) {
@@ -440,7 +452,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene s
                 kind = Q_FIRST_MAT + (uint32_t)sc.materials[m].kind;
             }
             e.hit = make_uint4(__float_as_uint(h.t), h.prim, h.inst, (uint32_t)m);
-            shade_entry(sc, rp, accum, nonfinite, kind, e, cont);
+            shade_entry<ALPHA>(sc, rp, accum, nonfinite, kind, e, cont);
             ++rays;
         }
     }
@@ -468,10 +480,11 @@ __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, 
             emat = pick_material(sc, m, key, kStreamEmit);
             mat = pick_material(sc, m, key, kStreamMix);
         }
-        Surfel s = resolve_hit(sc, ray, h, m);
+        Surfel s = resolve_hit<ALPHA>(sc, ray, h, m);
         V3 emitted = (emat.kind == MRT_MAT_DIFFUSE_LIGHT) ? V3{emat.p[0], emat.p[1], emat.p[2]} : V3{0.0f, 0.0f, 0.0f};
+        if (ALPHA && emat.kind == MRT_MAT_EVE && s.has_uv) emitted = eve_emission(sc, emat, s.u, s.v);
         ScatterOut sco;
-        scatter_kind(sc, mat, ray, s, draw4(key, kStreamScatter), sco);
+        scatter_kind<ALPHA>(sc, mat, ray, s, draw4(key, kStreamScatter), sco);
         a = sco.scattered ? sco.attenuation : emitted;
         n = s.normal;
         obj = s.object_id;
@@ -614,7 +627,7 @@ struct mrt_context {
     unsigned long long* d_count = nullptr;  // sample-count cell of the reduce
     unsigned long long* h_count = nullptr;  // pinned
     int grid_extend[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [count visits][0 plain, 1 volumes, 2 alpha-tested triangles (+ volumes)]
-    int grid_shade = 0, grid_generate = 0;
+    int grid_shade = 0, grid_shade_full = 0, grid_generate = 0;
 };
 
 static std::string g_create_error;
@@ -868,8 +881,10 @@ int mrt_context_create(int device, void* stream, mrt_context** out) {
     ctx->grid_extend[1][0] = extend_grid(k_extend<true, false, false>);
     ctx->grid_extend[1][1] = extend_grid(k_extend<true, false, true>);
     ctx->grid_extend[1][2] = extend_grid(k_extend<true, true, true>);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, MRT_SHADE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<false>, MRT_SHADE_THREADS, 0);
     ctx->grid_shade = ctx->n_sms * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<true>, MRT_SHADE_THREADS, 0);
+    ctx->grid_shade_full = ctx->n_sms * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_generate, 256, 0);
     ctx->grid_generate = ctx->n_sms * std::max(occ, 1);
     cudaDeviceSetLimit(cudaLimitStackSize, 2048);
@@ -1031,6 +1046,12 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
         bool ok = m.kind >= 0 && m.kind < MRT_MAT_KINDS;
         if (ok && (m.kind == MRT_MAT_LAMBERTIAN || m.kind == MRT_MAT_METAL || m.kind == MRT_MAT_SPECULAR)) ok = surf_ok(m.surface);
         if (ok && m.kind == MRT_MAT_MIX) ok = mat_ok(m.left, false) && mat_ok(m.right, false) && (uint64_t)m.left < i && (uint64_t)m.right < i;
+        if (ok && m.kind == MRT_MAT_EVE) {
+            int32_t pal;
+            std::memcpy(&pal, &m.p[0], 4);
+            ok = surf_ok(m.surface) && surf_ok(m.left) && surf_ok(m.right) && pal >= 0 && (uint64_t)pal + 4 <= s->n_surfaces;
+            for (int k = 0; ok && k < 4; ++k) ok = s->surfaces[pal + k].kind == MRT_SURF_SOLID;
+        }
         if (!ok) return fail(ctx, MRT_E_INVALID, "malformed material table entry " + std::to_string(i));
     }
     for (uint64_t i = 0; i < s->n_spheres; ++i)
@@ -1046,7 +1067,8 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     for (uint64_t i = 0; i < s->n_volumes; ++i) {
         const mrt_volume& v = s->volumes[i];
         if (!ref_ok(s, v.target, false)) return fail(ctx, MRT_E_INVALID, "volume target out of range");
-        if (MRT_REF_KIND(v.target) != MRT_PRIM_SPHERE) return fail(ctx, MRT_E_UNSUPPORTED, "only Volume<Sphere> is implemented");
+        if (MRT_REF_KIND(v.target) != MRT_PRIM_SPHERE && MRT_REF_KIND(v.target) != MRT_PRIM_INSTANCE)
+            return fail(ctx, MRT_E_UNSUPPORTED, "Volume targets: Sphere, Model and Instance (geom.rs:595 is generic over Intersect)");
         if (!mat_ok(v.material, false)) return fail(ctx, MRT_E_INVALID, "volume material out of range");
     }
     if (s->background.kind == MRT_BG_SKYSPHERE && !surf_ok(s->background.surface[0])) return fail(ctx, MRT_E_INVALID, "background surface out of range");
@@ -1393,6 +1415,10 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
     d.root = device_root;
     d.n_volumes = (uint32_t)s->n_volumes;
     d.has_alpha = any_alpha;
+    for (uint64_t i = 0; i < s->n_volumes; ++i)
+        if (MRT_REF_KIND(s->volumes[i].target) == MRT_PRIM_INSTANCE) d.has_alpha = 1;  // Volume over a mesh: only the full kernel variants carry that code
+    for (uint64_t i = 0; i < s->n_materials; ++i)
+        if (s->materials[i].kind == MRT_MAT_EVE) d.has_alpha = 1;  // likewise EveMaterial (tangent-space normals, texture-driven scatter and emission)
     d.bg = s->background;
     lap("copy");
     if (tlas_on_device) {  // ---- the TLAS of a world with many objects: boxes + references up, tree built on the GPU ---------
@@ -1664,7 +1690,8 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
                 else k_extend<false, false, false><<<grid, kExtendThreads, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur);
             }
             if (ctx->opt_time) { MRT_CUDA(cudaEventRecord(e[3], ctx->stream)); MRT_CUDA(cudaEventRecord(e[4], ctx->stream)); }
-            k_shade<<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite, rp.finish_paths);
+            if (mode == 2) k_shade<true><<<ctx->grid_shade_full, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite, rp.finish_paths);
+            else k_shade<false><<<ctx->grid_shade, MRT_SHADE_THREADS, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite, rp.finish_paths);
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[5], ctx->stream));
             cur ^= 1;
             st.kernel_launches += 3;

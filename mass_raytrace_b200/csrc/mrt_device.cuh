@@ -61,7 +61,7 @@ struct DScene {
     const float4* texels;
     uint32_t root;                       // the one root reference (node or single primitive); kNone = empty world
     uint32_t n_volumes;
-    uint32_t has_alpha;                  // some triangle carries kTriAlphaFlag
+    uint32_t has_alpha;                  // the scene needs the full intersection code (ALPHA variants): some triangle carries kTriAlphaFlag, or a Volume fills a mesh
     mrt_background bg;
 };
 struct DCamera {
@@ -208,7 +208,7 @@ __device__ __forceinline__ bool triangle_test(const DTriVerts& tv, const Ray& r,
 // interval by 2^-21 relatively. So the test never rejects a box the reference's test accepts, and nothing computed here reaches
 // a hit record. (A single slack for all axes would be wrong in practice: a ray almost parallel to an axis has |o * id| ~ 1e30
 // on that axis, and adding that to the other axes' intervals switches culling off for the whole ray.) A ray with d == 0 on an axis
-// ignores that axis (slab_axis below), which only accepts more.
+// is culled on that axis by where its origin lies (slab_axis below).
 struct SlabRay {
     V3 id;      // ~ 1 / direction
     V3 ood_lo;  // -(origin * id) -+ e: added to box.min * id
@@ -245,13 +245,9 @@ __device__ __forceinline__ Ray to_instance_space(const DInstance& in, const Ray&
     return Ray{xform(in.inv0, in.inv1, in.inv2, w.o, 1.0f), xform(in.inv0, in.inv1, in.inv2, w.d, 0.0f)};
 }
 
-// Volume::intersect geom.rs:612-655 for a sphere target. xi = the free-flight uniform (f32::rand(), :638).
-__device__ __forceinline__ bool volume_test(const DScene& sc, const mrt_volume& vol, const Ray& r, float t_min, float t_max, float xi, float& t_out) {
-    const float inf = __int_as_float(0x7f800000);
-    float4 s = __ldg(&sc.spheres[MRT_REF_INDEX(vol.target)]);
-    float enter, exit_;
-    if (!sphere_test(s, r, -inf, inf, enter)) return false;
-    if (!sphere_test(s, r, enter + 0.0001f, inf, exit_)) return false;
+// Volume::intersect geom.rs:612-655 after the two target.intersect calls: [enter, exit] clipped to [t_min, t_max], then the free flight.
+// xi = the free-flight uniform (f32::rand(), :638).
+__device__ __forceinline__ bool volume_flight(const mrt_volume& vol, const Ray& r, float enter, float exit_, float t_min, float t_max, float xi, float& t_out) {
     if (enter < t_min) enter = t_min;
     if (exit_ > t_max) exit_ = t_max;
     if (enter >= exit_) return false;
@@ -263,6 +259,15 @@ __device__ __forceinline__ bool volume_test(const DScene& sc, const mrt_volume& 
     t_out = enter + hit_distance / ray_length;
     return true;
 }
+// ... for a sphere target
+__device__ __forceinline__ bool volume_test(const DScene& sc, const mrt_volume& vol, const Ray& r, float t_min, float t_max, float xi, float& t_out) {
+    const float inf = __int_as_float(0x7f800000);
+    float4 s = __ldg(&sc.spheres[MRT_REF_INDEX(vol.target)]);
+    float enter, exit_;
+    if (!sphere_test(s, r, -inf, inf, enter)) return false;
+    if (!sphere_test(s, r, enter + 0.0001f, inf, exit_)) return false;
+    return volume_flight(vol, r, enter, exit_, t_min, t_max, xi, t_out);
+}
 
 // 1/x for the slab test only: one MUFU.RCP (<= 1 ulp, subnormals handled, 1/+-0 = +-inf). The slab test is widened by 4 ulp, which
 // covers this error; nothing that reaches a hit record uses it.
@@ -272,18 +277,23 @@ __device__ __forceinline__ float rcp_fast(float x) {
     return y;
 }
 __device__ __forceinline__ void slab_axis(float o, float d, float& id, float& ood_lo, float& ood_hi) {
-    id = rcp_fast(d);
+    // d == 0 (1 / d = +-inf) cannot go through b * id + ood: b * inf - o * inf is NaN whenever b and o have the same sign, and the
+    // reference's (b - o) / 0 = +-inf -- "inside this slab for all t, or for none" -- is lost. 1 / d is therefore capped at 2^100: the
+    // planes then sit at (b - o) * 2^100 -+ e, beyond every distance of a scene on the side the sign of b - o says, so a ray parallel
+    // to an axis is culled by whether its origin lies between the planes (to within the slack e, i.e. |o| 2^-21 in space). Capping a
+    // nonzero |d| < 2^-100 shortens |t| and only moves planes towards the origin's side of e; o * id cannot overflow below |o| = 2^27.
+    // (First version: NaNs dropped by fminf / fmaxf next to a -inf made every box straddling 0 on that axis a miss -- found by the
+    // per-pixel volume test on the centre row of an axis-aligned camera. Second version: such rays ignored the axis -- correct, but a
+    // Lambertian bounce straight up from the ground, direction exactly (0, 1, 0), then walked 250,000 nodes of the 1 M-triangle
+    // mesh: one ray, 0.28 s.)
+    const float kCap = 1.2676506e30f;  // 2^100
+    id = fmaxf(fminf(rcp_fast(d), kCap), -kCap);  // (a NaN becomes kCap; rays with a NaN direction never get here, trav_begin)
     const float p = o * id;
     const float e = fabsf(p) * 4.76837158203125e-7f;
     const float se = copysignf(e, id);  // d > 0: box.min is the near plane and gets -e
     ood_lo = -p - se;
     ood_hi = -p + se;
-    // d == 0 (id = +-inf), or d so small that o / d overflows: b * id + ood cannot express the reference's (b - o) / d = +-inf any
-    // more -- b * inf - o * inf is NaN whenever b and o have the same sign, and a dropped NaN next to a -inf made the far plane
-    // -inf, so that a ray exactly parallel to an axis missed every box straddling 0 on it (found by the per-pixel volume test: the
-    // centre row of an image whose camera looks along an axis). Such a ray ignores the axis instead: near -inf, far +inf for every
-    // finite plane, which only accepts more (the reference rejects when the origin lies outside the slab).
-    if (!(fabsf(p) < 3.0e38f) || !(fabsf(id) < 3.0e38f)) {
+    if (!(fabsf(p) < 3.0e38f)) {  // |o| >= 2^27 under a capped direction (or a NaN): the axis is ignored, which only accepts more
         id = 1.17549435e-38f;
         ood_lo = -__int_as_float(0x7f800000);
         ood_hi = __int_as_float(0x7f800000);
@@ -344,11 +354,11 @@ __device__ __forceinline__ void trav_begin(const DScene& sc, Traversal& T, W& ws
     T.cur_inst = kNone;
     T.ref = sc.root;  // kNone for an empty world
     T.inst_base = 0;
-    // A ray whose direction has no length or is not finite misses everything. (In the reference NaN compares false everywhere: such a
+    // A ray whose direction has no length or is not finite, or whose origin is not finite, misses everything. (In the reference NaN compares false everywhere: such a
     // ray passes every box test and "hits" the first sphere it meets at t = NaN, whichever that is in its tree, and keeps bouncing
     // as a NaN ray until the depth limit. Here it would walk the whole scene once per bounce -- measured: one such path, 0.47 s.)
-    const float len2 = length_squared(world.d);
-    if (!(len2 > 0.0f) || !(len2 < __int_as_float(0x7f800000))) T.ref = kNone;
+    const float len2 = length_squared(world.d), oabs = fabsf(world.o.x) + fabsf(world.o.y) + fabsf(world.o.z);
+    if (!(len2 > 0.0f) || !(len2 < __int_as_float(0x7f800000)) || !(oabs < __int_as_float(0x7f800000))) T.ref = kNone;
 }
 
 // false when the traversal is complete (T.best is final). Entries pushed before an instance was entered sit below
@@ -391,6 +401,84 @@ __device__ __forceinline__ void trav_node(const DScene& sc, Traversal& T, uint32
 
 // Material::alpha_test of the triangle's OWN material at the candidate hit (geom.rs:567-571); defined after the surfaces below
 __device__ bool triangle_alpha_test(const DScene& sc, const DTriVerts& tv, uint32_t tri_dev, const Ray& r, float t, const RngKey& key);
+
+// Closest triangle of one BLAS in [t_min, t_max] -- the smallest t, which may be negative: what Model / Instance::intersect returns to
+// Volume::intersect (geom.rs:613-619, :318-328, :404-420). `stk` is scratch for at least the BLAS's depth (the free part of the
+// caller's traversal stack).
+template <bool COUNT, bool ALPHA>
+__device__ __noinline__ bool blas_nearest(const DScene& sc, uint32_t root, const Ray& r, float t_min, float t_max, uint32_t* stk, const RngKey& key, VisitCounters* cnt,
+                                          float& t_out) {
+    const SlabRay s = slab_ray(r);
+    float best = t_max;
+    bool found = false;
+    int sp = 0;
+    uint32_t ref = root;
+    for (;;) {
+        if (ref == kNone) {
+            if (sp == 0) break;
+            ref = stk[--sp];
+        }
+        if (ref_is_node(ref)) {
+            const DNode* np = &sc.nodes[MRT_REF_INDEX(ref)];
+            DNode n;
+            n.xy0 = __ldg(&np->xy0);
+            n.xy1 = __ldg(&np->xy1);
+            n.z01 = __ldg(&np->z01);
+            const uint2 ch = __ldg(reinterpret_cast<const uint2*>(&np->child0));
+            if (COUNT) cnt->node_visits++;
+            bool h0, h1;
+            float n0, n1;
+            slab2(n, s, t_min, best, h0, h1, n0, n1);
+            h0 = h0 && ch.x != kNone;
+            h1 = h1 && ch.y != kNone;
+            if (h0 && h1) {
+                const bool swap = n1 < n0;
+                stk[sp++] = swap ? ch.x : ch.y;
+                ref = swap ? ch.y : ch.x;
+            } else {
+                ref = h0 ? ch.x : (h1 ? ch.y : kNone);
+            }
+        } else {  // a triangle leaf (a BLAS holds nothing else)
+            const uint32_t first = ref & kTriIndexMask, count = ((ref >> 27) & 3u) + 1u;
+            for (uint32_t k = 0; k < count; ++k) {
+                if (COUNT) cnt->tri_tests++;
+                const DTriVerts* tp = &sc.tri_verts[first + k];
+                DTriVerts tv;
+                tv.a = __ldg(&tp->a);
+                tv.b = __ldg(&tp->b);
+                tv.c = __ldg(&tp->c);
+                float t;
+                if (triangle_test(tv, r, t_min, best, t)) {
+                    if (ALPHA && (__float_as_uint(tv.a.w) & kTriAlphaFlag) && !triangle_alpha_test(sc, tv, first + k, r, t, key)) continue;
+                    best = t;
+                    found = true;
+                }
+            }
+            ref = kNone;
+        }
+    }
+    t_out = best;
+    return found;
+}
+// Volume::intersect for a Model / Instance target: the medium fills the mesh between its first crossing of the ray's line and the
+// next one (geom.rs:613-619: convex targets are what the construction is meant for)
+template <bool COUNT, bool ALPHA>
+__device__ __forceinline__ bool volume_test_mesh(const DScene& sc, const mrt_volume& vol, const Ray& r, float t_min, float t_max, float xi, uint32_t* stk,
+                                                 const RngKey& key, VisitCounters* cnt, float& t_out) {
+    const float inf = __int_as_float(0x7f800000);
+    const DInstance* ip = &sc.instances[MRT_REF_INDEX(vol.target)];
+    DInstance in;
+    in.inv0 = __ldg(&ip->inv0);
+    in.inv1 = __ldg(&ip->inv1);
+    in.inv2 = __ldg(&ip->inv2);
+    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(&ip->root));
+    in.flags = meta.z;
+    const Ray local = to_instance_space(in, r);  // t is the same along both rays (geom.rs:405-408: the direction is not normalised)
+    float enter, exit_;
+    if (!blas_nearest<COUNT, ALPHA>(sc, meta.x, local, -inf, inf, stk, key, cnt, enter)) return false;
+    if (!blas_nearest<COUNT, ALPHA>(sc, meta.x, local, enter + 0.0001f, inf, stk, key, cnt, exit_)) return false;
+    return volume_flight(vol, r, enter, exit_, t_min, t_max, xi, t_out);
+}
 
 // ALPHA = the scene has alpha-tested triangles, VOLUME = it has volumes: both draw random numbers during intersection (geom.rs:568,
 // :638) and so need the path's RNG key; scenes without them run the variant that carries no key and has neither code path.
@@ -445,7 +533,10 @@ __device__ __forceinline__ void trav_leaf(const DScene& sc, Traversal& T, uint32
                 mrt_volume vol = sc.volumes[idx];
                 Rand4 xi = draw4(key, kStreamVolume | (idx & kStreamIndexMask));
                 float t;
-                if (volume_test(sc, vol, T.r, t_min, T.best.t, xi.x, t)) T.best = HitRec{t, ref, kNone};
+                bool hit;
+                if (!ALPHA || MRT_REF_KIND(vol.target) == MRT_PRIM_SPHERE) hit = volume_test(sc, vol, T.r, t_min, T.best.t, xi.x, t);
+                else hit = volume_test_mesh<COUNT, ALPHA>(sc, vol, T.r, t_min, T.best.t, xi.x, stack + T.sp, key, cnt, t);  // (scenes with such volumes run the ALPHA variant)
+                if (hit) T.best = HitRec{t, ref, kNone};
             }
             break;
         }
@@ -546,6 +637,36 @@ __device__ __noinline__ V4 surface_get_slow(const DScene& sc, int surface, float
     }
 }
 
+// ---- EveMaterial (eve.rs:43-133): texture-driven Mix(Lambertian, Specular 1.8) with emission and tangent-space normals ------------
+__device__ __forceinline__ int eve_palette_surface(const mrt_material& m) { return __float_as_int(m.p[0]); }
+__device__ __noinline__ V3 eve_normal(const DScene& sc, const mrt_material& m, float u, float v) {  // normal_occlusion :66-73, normal :130-133
+    V4 px = surface_get(sc, m.surface, u, v);
+    float y = px.y * 2.0f - 1.0f, w = px.w * 2.0f - 1.0f;
+    float x = (1.0f - y * y) - w * w;
+    return unit(V3{y, w, sqrtf(fabsf(x))});
+}
+__device__ __forceinline__ V3 eve_palette(const DScene& sc, const mrt_material& m, float i) {  // EveMaterialColor::get :190-199
+    i = i * 3.0f;
+    uint32_t i0 = as_index(floorf(i), 4u), i1 = as_index(ceilf(i), 4u);
+    float t = i - (float)i0;
+    const mrt_surface &a = sc.surfaces[eve_palette_surface(m) + (int)i0], &b = sc.surfaces[eve_palette_surface(m) + (int)i1];
+    return (V3{a.color[0], a.color[1], a.color[2]} * (1.0f - t)) + (V3{b.color[0], b.color[1], b.color[2]} * t);
+}
+__device__ __noinline__ V3 eve_emission(const DScene& sc, const mrt_material& m, float u, float v) {  // emit :121-128: glow colour * glow mask * 10
+    const int p = eve_palette_surface(m);
+    return V3{sc.surfaces[p].color[3], sc.surfaces[p + 1].color[3], sc.surfaces[p + 2].color[3]} * surface_get(sc, m.right, u, v).w * 10.0f;
+}
+// colour and Mix ratio of the Lambertian / Specular pair the material builds per hit (scatter :91-119)
+__device__ __noinline__ void eve_surface(const DScene& sc, const mrt_material& m, float u, float v, V3& color, float& ratio) {
+    V4 ar = surface_get(sc, m.left, u, v);
+    V4 k = surface_get(sc, m.right, u, v);
+    V3 albedo{ar.x, ar.y, ar.z};
+    float paint = k.x, dirt = k.z * 1.0f;
+    V3 material_color = eve_palette(sc, m, k.y);
+    color = (((albedo * material_color * (1.0f - paint)) + (albedo * paint)) * (1.0f - fminf(dirt, 1.0f))) + (V3{0.01f, 0.005f, 0.0f} * dirt);
+    ratio = fminf(ar.w + dirt, 1.0f);
+}
+
 // Triangle::intersect's alpha test (geom.rs:535-571): area barycentrics -> uv -> alpha_test of the triangle's own material
 // (Lambertian / Metal / Specular: surface alpha != 0, material.rs:222-224, 281-283, 380-382; Mix: a coin flip then the child,
 // :419-425; every other material: the default `true`, :24-26).
@@ -596,6 +717,8 @@ __device__ __forceinline__ int32_t hit_material(const DScene& sc, const HitRec& 
         default: return -1;
     }
 }
+// FULL: the scene needs the rarely used code (an EveMaterial somewhere): compiled out of the kernels every other scene runs
+template <bool FULL>
 __device__ __forceinline__ Surfel resolve_hit(const DScene& sc, const Ray& world, const HitRec& h, int32_t material) {
     Surfel s;
     s.has_uv = false;
@@ -643,7 +766,12 @@ __device__ __forceinline__ Surfel resolve_hit(const DScene& sc, const Ray& world
                 s.has_uv = true;
                 s.u = (sh.uv[0] * a0 + sh.uv[2] * a1) + sh.uv[4] * a2;
                 s.v = (sh.uv[1] * a0 + sh.uv[3] * a1) + sh.uv[5] * a2;
-                // Material::normal is None for every material in material.rs (default :21-23): no tangent-space branch is reachable
+                // Material::normal of the triangle's OWN material (geom.rs:551-560); None for every material of material.rs (:21-23)
+                if (FULL && sc.materials[sh.material].kind == MRT_MAT_EVE) {
+                    const mrt_material own = sc.materials[sh.material];
+                    V3 tn = eve_normal(sc, own, s.u, s.v);
+                    normal = (v3(sh.tangent[0], sh.tangent[1], sh.tangent[2]) * tn.x + v3(sh.bitangent[0], sh.bitangent[1], sh.bitangent[2]) * tn.y) + normal * tn.z;
+                }
             }
             set_face_normal(s, r, normal);
             if (in.flags & MRT_INSTANCE_IDENTITY) {
@@ -738,7 +866,37 @@ __device__ __forceinline__ void lambertian_scatter(const DScene& sc, const mrt_m
     out.dir = dir;
     out.attenuation = surface_rgb(sc, mat.surface, s);
 }
+__device__ __forceinline__ void lambertian_scatter_color(const Surfel& s, V3 color, float xa, float xb, ScatterOut& out) {
+    V3 dir = s.normal + sample_unit_vector(xa, xb);
+    if (near_zero(dir)) dir = s.normal;
+    out.scattered = true;
+    out.dir = dir;
+    out.attenuation = color;
+}
+// EveMaterial::scatter eve.rs:91-119: Mix(min(roughness + dirt, 1), Lambertian(color), Specular(1.8, color)).scatter -- the coin is xi.w
+__device__ __noinline__ void eve_scatter(const DScene& sc, const mrt_material& mat, const Ray& ray, const Surfel& s, const Rand4& xi, ScatterOut& out) {
+    if (!s.has_uv) return;
+    V3 color;
+    float mix_ratio;
+    eve_surface(sc, mat, s.u, s.v, color, mix_ratio);
+    if (xi.w < mix_ratio) {
+        lambertian_scatter_color(s, color, xi.x, xi.y, out);
+    } else {  // Specular::scatter material.rs:352-378
+        float ratio = s.front_face ? 1.0f / 1.8f : 1.8f;
+        V3 ud = unit(ray.d);
+        float cos_theta = fminf(dot(-ud, s.normal), 1.0f);
+        float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        if (ratio * sin_theta > 1.0f || reflectance(cos_theta, ratio) > xi.x) {
+            out.scattered = true;
+            out.dir = reflect(ud, s.normal);
+            out.attenuation = V3{1.0f, 1.0f, 1.0f};
+        } else {
+            lambertian_scatter_color(s, color, xi.y, xi.z, out);
+        }
+    }
+}
 // Hit::emit + Hit::scatter (geom.rs:26-32) for a resolved material kind (never MIX)
+template <bool FULL>
 __device__ __forceinline__ void scatter_kind(const DScene& sc, const mrt_material& mat, const Ray& ray, const Surfel& s, const Rand4& xi, ScatterOut& out) {
     out.scattered = false;
     switch (mat.kind) {
@@ -773,6 +931,9 @@ __device__ __forceinline__ void scatter_kind(const DScene& sc, const mrt_materia
             }
             break;
         }
+        case MRT_MAT_EVE:
+            if (FULL) eve_scatter(sc, mat, ray, s, xi, out);
+            break;
         case MRT_MAT_ISOTROPIC:  // :439-444
             out.scattered = true;
             out.dir = sample_unit_ball(xi.x, xi.y, xi.z);

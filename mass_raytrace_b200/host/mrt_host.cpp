@@ -662,6 +662,16 @@ int mrth_mat_mix(mrth_scene* s, float ratio, int left, int right) {
     return push_material(s, MRT_MAT_MIX, -1, left, right, ratio, 0, 0, 0);
 }
 int mrth_mat_isotropic(mrth_scene* s, float r, float g, float b) { return push_material(s, MRT_MAT_ISOTROPIC, -1, -1, -1, r, g, b, 0); }
+// EveMaterial::new + EveMaterialColor (eve.rs:43-64, :135-199): three texture surfaces and the palette, flattened as mrt.h describes
+int mrth_mat_eve(mrth_scene* s, int normal_occlusion, int albedo_roughness, int pmdg, const float colors12[12], const float glow3[3]) {
+    for (int h : {normal_occlusion, albedo_roughness, pmdg})
+        if (h < 0 || (size_t)h >= s->surfaces.size()) { s->err = "invalid surface handle"; return MRT_E_INVALID; }
+    const int palette = (int)s->surfaces.size();
+    for (int i = 0; i < 4; ++i) mrth_surface_solid(s, colors12[3 * i], colors12[3 * i + 1], colors12[3 * i + 2], i < 3 ? glow3[i] : 0.0f);
+    float bits;
+    std::memcpy(&bits, &palette, 4);
+    return push_material(s, MRT_MAT_EVE, normal_occlusion, albedo_roughness, pmdg, bits, 0, 0, 0);
+}
 
 void mrth_background_solid(mrth_scene* s, float r, float g, float b) {
     s->bg = mrt_background{};
@@ -804,7 +814,9 @@ int mrth_add_sphere(mrth_scene* s, int material, float cx, float cy, float cz, f
     s->spheres.push_back(sp);
     return push_object(s, MRT_REF(MRT_PRIM_SPHERE, s->spheres.size() - 1));
 }
-static int add_instance_common(mrth_scene* s, int mesh, const Mat4& fwd, const Mat4& inv, uint32_t flags, int material) {
+// as_object: the instance is an object of the world (World::add); otherwise it is the target of a Volume and only the Volume is
+// (returns the instance index then)
+static int add_instance_common(mrth_scene* s, int mesh, const Mat4& fwd, const Mat4& inv, uint32_t flags, int material, bool as_object = true) {
     if (mesh < 0 || (size_t)mesh >= s->blas.size()) { s->err = "invalid mesh handle"; return MRT_E_INVALID; }
     if (!valid_material(s, material, true)) return MRT_E_INVALID;
     mrt_instance in{};
@@ -829,23 +841,43 @@ static int add_instance_common(mrth_scene* s, int mesh, const Mat4& fwd, const M
     in.blas = (uint32_t)mesh;
     in.material = material;
     in.flags = flags;
-    in.object_id = (uint32_t)s->objects.size();
+    in.object_id = as_object ? (uint32_t)s->objects.size() : MRT_REF_NONE;
     s->instances.push_back(in);
+    if (!as_object) return (int)s->instances.size() - 1;
     return push_object(s, MRT_REF(MRT_PRIM_INSTANCE, s->instances.size() - 1));
 }
 int mrth_add_model(mrth_scene* s, int mesh, int override_material) {
     return add_instance_common(s, mesh, mat_identity(), mat_identity(), MRT_INSTANCE_IDENTITY, override_material);
 }
-int mrth_add_instance(mrth_scene* s, int mesh, const float t[3], const float r[3], const float sc[3], int override_material) {
+static void instance_matrices(const float t[3], const float r[3], const float sc[3], Mat4& fwd, Mat4& inv) {
     // Instance::new geom.rs:343-367
     Vec3 tr = load3(t), rot = load3(r), scl = load3(sc);
     Vec3 inv_tr = scale(tr, -1.0f), inv_rot = scale(rot, -1.0f);
     Vec3 inv_scl{1.0f / scl.x, 1.0f / scl.y, 1.0f / scl.z};
     Mat4 rotation = mat_mul(mat_mul(mat_rotate(0, rot.x), mat_rotate(1, rot.y)), mat_rotate(2, rot.z));
     Mat4 inv_rotation = mat_mul(mat_mul(mat_rotate(2, inv_rot.z), mat_rotate(1, inv_rot.y)), mat_rotate(0, inv_rot.x));
-    Mat4 fwd = mat_mul(mat_mul(mat_translation(tr), rotation), mat_scale(scl));
-    Mat4 inv = mat_mul(mat_mul(mat_scale(inv_scl), inv_rotation), mat_translation(inv_tr));
+    fwd = mat_mul(mat_mul(mat_translation(tr), rotation), mat_scale(scl));
+    inv = mat_mul(mat_mul(mat_scale(inv_scl), inv_rotation), mat_translation(inv_tr));
+}
+int mrth_add_instance(mrth_scene* s, int mesh, const float t[3], const float r[3], const float sc[3], int override_material) {
+    Mat4 fwd, inv;
+    instance_matrices(t, r, sc, fwd, inv);
     return add_instance_common(s, mesh, fwd, inv, 0, override_material);
+}
+// Volume::new(target, density, albedo) geom.rs:601-609 over a Model or an Instance of a mesh
+static int add_volume_over(mrth_scene* s, int target_instance, float density, float r, float g, float b) {
+    if (target_instance < 0) return target_instance;
+    mrt_volume v{MRT_REF(MRT_PRIM_INSTANCE, (uint32_t)target_instance), -1.0f / density, mrth_mat_isotropic(s, r, g, b), (uint32_t)s->objects.size()};
+    s->volumes.push_back(v);
+    return push_object(s, MRT_REF(MRT_PRIM_VOLUME, s->volumes.size() - 1));
+}
+int mrth_add_volume_model(mrth_scene* s, int mesh, float density, float r, float g, float b) {
+    return add_volume_over(s, add_instance_common(s, mesh, mat_identity(), mat_identity(), MRT_INSTANCE_IDENTITY, -1, false), density, r, g, b);
+}
+int mrth_add_volume_instance(mrth_scene* s, int mesh, const float t[3], const float rot[3], const float sc[3], float density, float r, float g, float b) {
+    Mat4 fwd, inv;
+    instance_matrices(t, rot, sc, fwd, inv);
+    return add_volume_over(s, add_instance_common(s, mesh, fwd, inv, 0, -1, false), density, r, g, b);
 }
 int mrth_add_volume_sphere(mrth_scene* s, float cx, float cy, float cz, float radius, float density, float r, float g, float b) {
     int absorb = mrth_mat_absorb(s);  // Sphere<()> target (scenes/eve.rs:41-45)

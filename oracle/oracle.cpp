@@ -429,6 +429,52 @@ struct Mix : Material {  // material.rs:391-426 — independent coin flips in sc
     bool emit(const Hit& hit, V3& out) const override { return (frand() < ratio) ? left->emit(hit, out) : right->emit(hit, out); }
     bool alpha_test(V2 uv) const override { return (frand() < ratio) ? left->alpha_test(uv) : right->alpha_test(uv); }
 };
+// eve.rs:23-199 — the one material of the reference that implements Material::normal (the tangent-space hook of Triangle::intersect,
+// geom.rs:551-560): three textures (normal + occlusion, albedo + roughness, paint / material / dirt / glow masks) and a palette.
+struct EveMaterial : Material {
+    const Surface *normal_occlusion, *albedo_roughness, *pmdg;
+    V3 colors[4], glow;
+    EveMaterial(const Surface* no, const Surface* ar, const Surface* p, const V3 c[4], V3 g) : normal_occlusion(no), albedo_roughness(ar), pmdg(p), glow(g) {
+        for (int i = 0; i < 4; ++i) colors[i] = c[i];
+    }
+    V3 palette(F i) const {  // EveMaterialColor::get :190-199
+        i = i * 3.0f;
+        F f0 = std::floor(i), f1 = std::ceil(i);
+        size_t i0 = f0 > 0.0f ? (size_t)f0 : 0, i1 = f1 > 0.0f ? (size_t)f1 : 0;  // `as usize` saturates at 0; the reference panics past the palette
+        if (i0 > 3) i0 = 3;
+        if (i1 > 3) i1 = 3;
+        F t = i - (F)i0;
+        return colors[i0] * (1.0f - t) + colors[i1] * t;
+    }
+    bool scatter(const Ray& ray, const Hit& hit, Scatter& out) const override {  // :91-119
+        if (!hit.has_uv) return false;
+        V4 ar = albedo_roughness->get_f(hit.uv);
+        V3 albedo = contract(ar);
+        F roughness = ar.w;
+        V4 m = pmdg->get_f(hit.uv);
+        F paint = m.x, material = m.y, dirt = m.z * 1.0f;
+        V3 material_color = palette(material);
+        V3 color = (((albedo * material_color * (1.0f - paint)) + (albedo * paint)) * (1.0f - fmin_(dirt, 1.0f))) + (V3{0.01f, 0.005f, 0.0f} * dirt);
+        SolidColor solid(V4{color.x, color.y, color.z, 1.0f});
+        Lambertian lambertian(&solid);
+        Specular specular(1.8f, &solid);
+        Mix mix(fmin_(roughness + dirt, 1.0f), &lambertian, &specular);
+        return mix.scatter(ray, hit, out);
+    }
+    bool emit(const Hit& hit, V3& out) const override {  // :121-128
+        if (!hit.has_uv) return false;
+        out = glow * pmdg->get_f(hit.uv).w * 10.0f;
+        return true;
+    }
+    bool normal(V2 uv, V3& out) const override {  // :130-133 with normal_occlusion :66-73
+        V4 pixel = normal_occlusion->get_f(uv);
+        pixel = pixel * 2.0f - V4{1.0f, 1.0f, 1.0f, 1.0f};
+        F x = 1.0f - pixel.y * pixel.y - pixel.w * pixel.w;  // powi(2)
+        F z = std::sqrt(std::fabs(x));
+        out = unit(V3{pixel.y, pixel.w, z});
+        return true;
+    }
+};
 struct Isotrophic : Material {  // material.rs:428-445
     V3 albedo;
     explicit Isotrophic(V3 a) : albedo(a) {}
@@ -1463,6 +1509,11 @@ int orc_mat_dielectric(orc_scene* s, float ior) { return push_material(s, new Di
 int orc_mat_specular(orc_scene* s, float ior, int surface) { return push_material(s, new Specular(ior, surf(s, surface))); }
 int orc_mat_mix(orc_scene* s, float ratio, int l, int r) { return push_material(s, new Mix(ratio, mat(s, l), mat(s, r))); }
 int orc_mat_isotropic(orc_scene* s, float r, float g, float b) { return push_material(s, new Isotrophic({r, g, b})); }
+int orc_mat_eve(orc_scene* s, int no, int ar, int pmdg, const float colors12[12], const float glow3[3]) {
+    V3 c[4];
+    for (int i = 0; i < 4; ++i) c[i] = {colors12[3 * i], colors12[3 * i + 1], colors12[3 * i + 2]};
+    return push_material(s, new EveMaterial(surf(s, no), surf(s, ar), surf(s, pmdg), c, {glow3[0], glow3[1], glow3[2]}));
+}
 
 void orc_background_solid(orc_scene* s, float r, float g, float b) { s->world.background.reset(new SolidBackground({r, g, b})); }
 void orc_background_sky(orc_scene* s) { s->world.background.reset(new SkyBackground()); }
@@ -1595,6 +1646,18 @@ int orc_add_instance(orc_scene* s, int mesh, const float t[3], const float r[3],
 int orc_add_volume_sphere(orc_scene* s, float cx, float cy, float cz, float radius, float density, float r, float g, float b) {
     static Absorb unit_material;  // Sphere<()> scenes/eve.rs:41-45
     Volume* v = new Volume(new Sphere(&unit_material, {cx, cy, cz}, radius), density, {r, g, b});
+    int id = add_object(s, v);
+    v->object = (uint32_t)id;
+    return id;
+}
+int orc_add_volume_model(orc_scene* s, int mesh, float density, float r, float g, float b) {  // Volume::new(Model::new(..), ..) geom.rs:601-609
+    Volume* v = new Volume(new Model(s->meshes.at((size_t)mesh)->bvh.get(), nullptr), density, {r, g, b});
+    int id = add_object(s, v);
+    v->object = (uint32_t)id;
+    return id;
+}
+int orc_add_volume_instance(orc_scene* s, int mesh, const float t[3], const float rot[3], const float sc[3], float density, float r, float g, float b) {
+    Volume* v = new Volume(new Instance(s->meshes.at((size_t)mesh)->bvh.get(), v3(t), v3(rot), v3(sc), nullptr), density, {r, g, b});
     int id = add_object(s, v);
     v->object = (uint32_t)id;
     return id;

@@ -58,6 +58,7 @@ int orc_mat_dielectric(orc_scene*, float ior);                        /* :286 */
 int orc_mat_specular(orc_scene*, float ior, int surface);             /* :331 */
 int orc_mat_mix(orc_scene*, float ratio, int left, int right);        /* :391 */
 int orc_mat_isotropic(orc_scene*, float r, float g, float b);         /* Isotrophic :428 */
+int orc_mat_eve(orc_scene*, int normal_occlusion, int albedo_roughness, int pmdg, const float colors12[12], const float glow3[3]); /* EveMaterial eve.rs:43-133 */
 
 /* backgrounds  material.rs:39-190 */
 void orc_background_solid(orc_scene*, float r, float g, float b);
@@ -92,6 +93,8 @@ int orc_add_sphere(orc_scene*, int material, float cx, float cy, float cz, float
 int orc_add_model(orc_scene*, int mesh, int override_material);                                         /* World::add(Model), -1 = None */
 int orc_add_instance(orc_scene*, int mesh, const float t[3], const float r[3], const float s[3], int override_material); /* Model::instance().with_material() */
 int orc_add_volume_sphere(orc_scene*, float cx, float cy, float cz, float radius, float density, float r, float g, float b); /* Volume::new(Sphere<()>) :603 */
+int orc_add_volume_model(orc_scene*, int mesh, float density, float r, float g, float b);                                    /* Volume::new(Model) */
+int orc_add_volume_instance(orc_scene*, int mesh, const float t[3], const float rot[3], const float sc[3], float density, float r, float g, float b); /* Volume::new(Instance) */
 void orc_build_bvh(orc_scene*);                                        /* World::build_bvh world.rs:117 */
 uint64_t orc_tlas_node_count(orc_scene*);
 void orc_camera(orc_scene*, float vfov, const float from[3], const float at[3], const float up[3], float aspect, float aperture, float focus); /* Camera::new world.rs:16 */

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from mass_raytrace_b200 import (BLEND_ADDITION, WRAP_CLAMP, WRAP_REPEAT, Camera, CubeMap, Dielectric, DiffuseLight, Lambertian, Metal, Mix, Model, NativeScene,
+from mass_raytrace_b200 import (BLEND_ADDITION, WRAP_CLAMP, WRAP_REPEAT, EveMaterial, Camera, CubeMap, Dielectric, DiffuseLight, Lambertian, Metal, Mix, Model, NativeScene,
                                 SkyBackground, SkySphere, SolidBackground, SolidColor, SolidColorFallback, Specular, Sphere, Texture, TextureBlend, V3, V3_fill,
                                 Volume, World, YCbCrTexture, scenes)
 from mass_raytrace_b200.api import Volume as VolumeT
@@ -527,6 +527,107 @@ def test_dense_and_thin_volume(renderer):
     thin.build_bvh()
     renderer.set_scene(NativeScene(thin, cam))
     assert (renderer.render_aov(33, 33)["object"] == NONE).all()
+
+
+def test_volume_over_model_and_instance_targets(renderer):
+    """Volume<I: Intersect> (geom.rs:595-660) with a mesh as the target: the medium fills a Model (a UV sphere mesh, no transform) and a
+    rotated, scaled Instance of the cube. Dense media: the primary ray scatters right behind the surface it enters through; media of
+    moderate density: per-pixel hit frequencies over 48 seeds agree with the oracle's like two samples of one probability; converged
+    renders agree statistically."""
+    from mass_raytrace_b200 import PlyLoader
+    cam = Camera(30.0, V3(0, 1.2, 7), V3(0, 0.9, 0), V3(0, 1, 0), 1.5, 0.0, 7.0)
+
+    def build(density):
+        w = World(SolidBackground(V3(0.9, 0.95, 1.0)))
+        w.add(Sphere(Lambertian(SolidColor((0.5, 0.5, 0.5, 1))), V3(0, -1000, 0), 1000.0))
+        ball = Model(scenes.uv_sphere_triangles((-1.3, 1.0, 0.0), 0.9, 24, 12, material=()))
+        w.add(Volume(ball, density, V3(0.8, 0.3, 0.2)))
+        cube = Model(PlyLoader.load(scenes.CUBE_PLY))
+        w.add(Volume(cube.instance(V3(1.3, 0.9, 0.0), V3(0.3, 0.6, 0.1), V3(0.8, 0.8, 0.8)), density, V3(0.2, 0.4, 0.8)))
+        w.add(Sphere(Metal(0.0, SolidColor((0.9, 0.9, 0.9, 1))), V3(0, 0.5, -2.5), 0.5))
+        w.build_bvh()
+        return w
+
+    W, H = 150, 100
+    # dense: the hit is the Volume, t just behind the entry surface, normal (1, 0, 0) (geom.rs:644-651)
+    w = build(1.0e4)
+    empty = build(1.0e-7)
+    renderer.set_scene(NativeScene(w, cam))
+    g = renderer.render_aov(W, H, seed=3)
+    o = OracleScene(w, cam).render_aov(W, H, seed=3)
+    vols = [1, 2]
+    gm, om = np.isin(g["object"], vols), np.isin(o["object"], vols)
+    assert 0.08 < om.mean() < 0.5
+    assert (gm != om).mean() < 0.002  # silhouette pixels whose chord is shorter than a free flight
+    both = gm & om
+    assert np.array_equal(g["object"][both], o["object"][both])
+    assert np.abs(g["t"][both] - o["t"][both]).max() < 5e-3 and (g["normal"][both] == np.array([1, 0, 0], np.float32)).all()
+    check_aov(g, o, exclude=gm | om, albedo_exact=False)
+    renderer.set_scene(NativeScene(empty, cam))
+    assert not np.isin(renderer.render_aov(W, H)["object"], vols).any()
+    # moderate density: per-pixel frequencies over many seeds
+    w = build(0.9)
+    renderer.set_scene(NativeScene(w, cam))
+    orc = OracleScene(w, cam)
+    n_seeds = 48
+    fg, fo = np.zeros((H, W)), np.zeros((H, W))
+    for seed in range(1, n_seeds + 1):
+        fg += np.isin(renderer.render_aov(W, H, seed=seed)["object"], vols)
+        fo += np.isin(orc.render_aov(W, H, seed=500 + seed)["object"], vols)
+    a, b = fg / n_seeds, fo / n_seeds
+    p = 0.5 * (a + b)
+    assert np.array_equal(p > 0, (a > 0) | (b > 0)) or ((p > 0) != ((a > 0) & (b > 0))).mean() < 0.01
+    mid = (p > 0.1) & (p < 0.9)
+    assert mid.sum() > 500
+    z = (a[mid] - b[mid]) / np.sqrt(2.0 * p[mid] * (1.0 - p[mid]) / n_seeds)
+    assert np.abs(z).max() < 6.0 and 0.75 < float(np.mean(z * z)) < 1.3, (float(np.abs(z).max()), float(np.mean(z * z)))
+    assert abs(float(np.mean(z))) < 5.0 / np.sqrt(mid.sum())
+    stat_compare(renderer, w, cam, 72, 48, 96)
+
+
+def eve_scene(seed=7, flat_normals=False):
+    """UV meshes carrying an EveMaterial (eve.rs:23-133): normal + occlusion, albedo + roughness and paint / material / dirt / glow
+    textures, tangent-space normals through Material::normal (geom.rs:551-560)."""
+    rs = np.random.RandomState(seed)
+    no = rs.randint(64, 192, (16, 32, 4)).astype(np.uint8)  # normal x in G, y in A (normal_occlusion :66-73); moderate tilts
+    if flat_normals:
+        no[..., 1] = 128
+        no[..., 3] = 128
+    ar = rs.randint(40, 256, (8, 16, 4)).astype(np.uint8)
+    pmdg = rs.randint(0, 256, (8, 8, 4)).astype(np.uint8)
+    pmdg[..., 2] //= 3       # little dirt
+    pmdg[..., 3] //= 8       # faint glow
+    eve = EveMaterial(Texture(no, WRAP_REPEAT), Texture(ar, WRAP_REPEAT), Texture(pmdg, WRAP_REPEAT))
+    w = World(SkyBackground())
+    w.add(Sphere(Lambertian(SolidColor((0.5, 0.5, 0.5, 1))), V3(0, -1000, 0), 1000.0))
+    w.add(Model(scenes.uv_sphere_triangles((-1.1, 1.0, 0.0), 1.0, 32, 16, material=eve)))
+    ship = Model(scenes.uv_sphere_triangles((0.0, 0.0, 0.0), 1.0, 24, 12, material=eve))
+    w.add(ship.instance(V3(1.2, 0.8, 0.3), V3(0.2, 0.7, 0.1), V3(0.9, 0.6, 0.7)))
+    w.build_bvh()
+    cam = Camera(35.0, V3(0, 2.0, 7), V3(0, 0.9, 0), V3(0, 1, 0), 1.5, 0.0, 7.0)
+    return w, cam
+
+
+def test_eve_material_tangent_space_normals(renderer):
+    w, cam = eve_scene()
+    renderer.set_scene(NativeScene(w, cam))
+    g = renderer.render_aov(300, 200)
+    o = OracleScene(w, cam).render_aov(300, 200)
+    check_aov(g, o, albedo_exact=False)  # the normals include the texture's tilt: bit-identical like everything else in a hit record
+    on_mesh = np.isin(o["object"], [1, 2]) & (g["tri"] == o["tri"])
+    assert on_mesh.sum() > 5000
+    # the same meshes with a flat normal map: the hook returns (0, 0, 1) and the shading normal is the interpolated one
+    wf, _ = eve_scene(flat_normals=True)
+    renderer.set_scene(NativeScene(wf, cam))
+    f = renderer.render_aov(300, 200)
+    tilted = np.abs(g["normal"] - f["normal"]).max(-1) > 1e-3
+    assert tilted[on_mesh].mean() > 0.9 and not tilted[~np.isin(o["object"], [1, 2])].any()
+    assert np.array_equal(f["t"], g["t"])
+    # albedo_normal's albedo (world.rs:81-93) is the scatter attenuation: a Mix coin decides between the surface colour and (1, 1, 1), so
+    # only its distribution can agree; emission and colour are covered by the converged render
+    stat_compare(renderer, w, cam, 90, 60, 128)
+    r = renderer.render(90, 60, 64, 50, seed=3)
+    assert renderer.stats()["rays"] > 90 * 60 * 64 * 1.5
 
 
 def test_resolve_rgb8_matches_reference_tonemap(renderer, oracle):

@@ -103,3 +103,31 @@ def test_volume_statistics():
     thin.build_bvh()
     s2 = OracleScene(thin, Camera(30.0, V3(0, 0, 4), V3(0, 0, 0), V3(0, 1, 0), 1.0, 0.0, 4.0))
     assert (s2.render_aov(9, 9)["object"] == 0xFFFFFFFF).all()  # free flight ~1e6 >> 2: passes through
+
+
+def test_volume_over_a_mesh_target():
+    """Volume<I: Intersect> with a Model / Instance target (geom.rs:595-660): a very dense medium scatters right behind the surface the
+    ray enters through, a very thin one never; the bounding box is the target's; a ray that starts inside is clipped at its origin."""
+    from mass_raytrace_b200 import Model, PlyLoader, NativeScene
+    cube = Model(PlyLoader.load(scenes.CUBE_PLY))  # [-1, 1]^3 (models/cube.ply)
+    cam = Camera(30.0, V3(0, 0, 6), V3(0, 0, 0), V3(0, 1, 0), 1.0, 0.0, 6.0)
+    for target, front in ((cube, 5.0 / 6.0), (cube.instance(V3(0, 0, 0.5), V3(0, 0, 0), V3(0.5, 0.5, 0.5)), 5.0 / 6.0)):  # t counts focus distances (world.rs:59)
+        w = World(SolidBackground(V3(1, 1, 1)))
+        w.add(Volume(target, 1.0e5, V3(0.5, 0.5, 0.5)))
+        w.build_bvh()
+        a = OracleScene(w, cam).render_aov(33, 33)
+        assert a["object"][16, 16] == 0 and abs(a["t"][16, 16] - front) < 1e-3 and a["normal"][16, 16].tolist() == [1, 0, 0]
+        assert a["object"][0, 0] == 0xFFFFFFFF
+        host = NativeScene(w, cam)
+        d = host.desc().contents
+        assert d.n_volumes == 1 and d.n_instances == 1 and d.n_roots == 1  # the target is not an object of the world itself
+        thin = World(SolidBackground(V3(1, 1, 1)))
+        thin.add(Volume(target, 1.0e-7, V3(0.5, 0.5, 0.5)))
+        thin.build_bvh()
+        assert (OracleScene(thin, cam).render_aov(33, 33)["object"] == 0xFFFFFFFF).all()
+    inside = Camera(60.0, V3(0, 0, 0), V3(0, 0, -1), V3(0, 1, 0), 1.0, 0.0, 1.0)
+    w = World(SolidBackground(V3(1, 1, 1)))
+    w.add(Volume(cube, 50.0, V3(0.5, 0.5, 0.5)))
+    w.build_bvh()
+    a = OracleScene(w, inside).render_aov(17, 17)
+    assert (a["object"] == 0).all() and (a["t"] < 0.5).all() and (a["t"] >= 0).all(), (a["t"].min(), a["t"].max())
