@@ -290,13 +290,14 @@ def main():
                     stats.append(st)
             total_ms = allreduce([sum(ms)], dist.ReduceOp.MAX)[0]
             sums = allreduce([sum(s["paths"] for s in stats), sum(s["rays"] for s in stats), sum(s["kernel_launches"] for s in stats)], dist.ReduceOp.SUM)
+            timed.last_steps_ms = [round(x, 3) for x in ms]  # this rank's steps one by one: a step far off the others is a path that met a pathological ray
             return total_ms / 1e3, sums
 
         # ---- device-resident timing (strong scaling) ------------------------------------------------------------------------
         total_s, (paths, rays, launches) = timed(warmup, steps)
         rec = {"value": paths / total_s / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays / total_s / 1e6, "ms_per_step": 1e3 * total_s / steps, "steps": steps,
                "warmup": warmup, "workload": f"configs[{cfg}]: {desc}", "width": w, "height": h, "spp_per_step": spp, "rays_per_path": rays / max(paths, 1),
-               "scene_build_s": build_s}
+               "scene_build_s": build_s, "steps_ms": timed.last_steps_ms}
         rec["_launches"] = launches + (4 * world_size * steps if world_size > 1 else 0)  # + fold / cell / 2 NCCL kernels / unfold per rank and step
 
         # ---- roofline of the dominant kernel (extend) -------------------------------------------------------------------------
