@@ -278,26 +278,22 @@ __device__ __forceinline__ float rcp_fast(float x) {
 }
 __device__ __forceinline__ void slab_axis(float o, float d, float& id, float& ood_lo, float& ood_hi) {
     // d == 0 (1 / d = +-inf) cannot go through b * id + ood: b * inf - o * inf is NaN whenever b and o have the same sign, and the
-    // reference's (b - o) / 0 = +-inf -- "inside this slab for all t, or for none" -- is lost. 1 / d is therefore capped at 2^100: the
-    // planes then sit at (b - o) * 2^100 -+ e, beyond every distance of a scene on the side the sign of b - o says, so a ray parallel
+    // reference's (b - o) / 0 = +-inf -- "inside this slab for all t, or for none" -- is lost. 1 / d is therefore capped at 2^64: the
+    // planes then sit at (b - o) * 2^64 -+ e, beyond every distance of a scene on the side the sign of b - o says, so a ray parallel
     // to an axis is culled by whether its origin lies between the planes (to within the slack e, i.e. |o| 2^-21 in space). Capping a
-    // nonzero |d| < 2^-100 shortens |t| and only moves planes towards the origin's side of e; o * id cannot overflow below |o| = 2^27.
+    // nonzero |d| < 2^-64 shortens |t| and only moves planes towards the origin's side of e. o * id stays finite below |o| = 2^63
+    // (coordinates no float scene has).
     // (First version: NaNs dropped by fminf / fmaxf next to a -inf made every box straddling 0 on that axis a miss -- found by the
     // per-pixel volume test on the centre row of an axis-aligned camera. Second version: such rays ignored the axis -- correct, but a
     // Lambertian bounce straight up from the ground, direction exactly (0, 1, 0), then walked 250,000 nodes of the 1 M-triangle
     // mesh: one ray, 0.28 s.)
-    const float kCap = 1.2676506e30f;  // 2^100
+    const float kCap = 1.8446744e19f;  // 2^64
     id = fmaxf(fminf(rcp_fast(d), kCap), -kCap);  // (a NaN becomes kCap; rays with a NaN direction never get here, trav_begin)
     const float p = o * id;
     const float e = fabsf(p) * 4.76837158203125e-7f;
     const float se = copysignf(e, id);  // d > 0: box.min is the near plane and gets -e
     ood_lo = -p - se;
     ood_hi = -p + se;
-    if (!(fabsf(p) < 3.0e38f)) {  // |o| >= 2^27 under a capped direction (or a NaN): the axis is ignored, which only accepts more
-        id = 1.17549435e-38f;
-        ood_lo = -__int_as_float(0x7f800000);
-        ood_hi = __int_as_float(0x7f800000);
-    }
 }
 __device__ __forceinline__ SlabRay slab_ray(const Ray& r) {
     SlabRay s;
