@@ -9,8 +9,8 @@ A step = one pass of the hot path over one batch: the workload's image at the wo
 samples of every pixel are SPLIT over the ranks (strong scaling: the job is the same at every N, `distributed.sample_range`),
 each rank accumulates its share into its exact int64 image and ONE NCCL sum-reduce inside the library (mrt_comm_*, include/mrt.h)
 merges them onto rank 0 before the step ends. `value` = paths of the whole job / max-over-ranks device time, inputs resident in
-HBM. `e2e` = the same through the C ABI with host buffers: scene + camera upload, render, reduce, device->host copy of the
-image, all inside the timed region. The headline workload is configs[2] (the 1 M-triangle mesh north_star names); the other
+HBM. `e2e` = the same through the C ABI with host buffers: scene + camera upload (with N ranks the root uploads and builds once and
+the library broadcasts the device arrays over NVLink), render, reduce, device->host copy of the image, all inside the timed region. The headline workload is configs[2] (the 1 M-triangle mesh north_star names); the other
 BASELINE configs are measured in the same run with fewer steps and reported under `per_config`. `parity` = a fixed small job of
 the headline scene rendered by all ranks together: its SHA-256 must be the same at every N, and rank 0 checks it against the
 CPU oracle. Prints ONE JSON line (rank 0).
@@ -359,7 +359,7 @@ def main():
                 flush.zero_()
             barrier()
             t0 = time.perf_counter()
-            r.set_scene(host)  # H2D: flattened scene + camera, every step
+            r.set_scene(host)  # H2D: flattened scene + camera, every step (N > 1: rank 0 uploads and builds, the finished arrays are broadcast over NVLink)
             with torch.cuda.stream(stream):
                 r.render(w, h, spp, 50, seed=2024, spp_begin=((2000 + i) * spp) % (1 << 30), out=(rgb_np, b_np))  # render (+ reduce) + D2H on the root
             barrier()
@@ -367,7 +367,7 @@ def main():
                 e2e_t.append(time.perf_counter() - t0)
         e2e_s = allreduce([sum(e2e_t)], dist.ReduceOp.MAX)[0]
         scene_bytes = r.stats()["scene_bytes"] + 76
-        rec["e2e"] = {"value": (npix * spp * len(e2e_t)) / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes) * world_size,
+        rec["e2e"] = {"value": (npix * spp * len(e2e_t)) / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes) + 76 * (world_size - 1),
                       "d2h_bytes_per_step": int(npix * 16), "ms_per_step": 1e3 * e2e_s / len(e2e_t), "steps": len(e2e_t)}
 
         if detail and world_size > 1:  # weak scaling beside it: every rank renders the config's full spp, N x the samples per step

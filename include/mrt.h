@@ -308,6 +308,9 @@ enum {
                                   lattices): worth it for renders of thousands of samples per pixel */
     MRT_OPT_NODE_BURST = 12,   /* k_extend: at most this many node visits per lane before the warp tests its pending leaves; 0 (default) = by scene:
                                   no bound, or 4 when a mesh's tree is deep */
+    MRT_OPT_COMM_SCENE = 14,   /* 1 (default): on a one-process-per-GPU communicator mrt_scene_upload is COLLECTIVE -- rank 0 validates, builds and
+                                  uploads its scene once and the finished device arrays are broadcast over NVLink (the other ranks' desc is not
+                                  read and may be NULL); 0: every rank uploads its own host copy */
     MRT_OPT_BVH_LEAF_TRIS = 9, /* SAH rebuild at the next mrt_scene_upload: most triangles per BLAS leaf, 1..4 (default 4) */
     MRT_OPT_BVH_TRI_COST = 10, /* SAH rebuild: cost of one triangle test in hundredths of a node visit (default 100) */
     MRT_OPT_COMM_SPLIT = 13,   /* 1 (default): on a context with a communicator mrt_render_accumulate splits the sample range and merges; 0: it renders

@@ -542,7 +542,7 @@ class Renderer:
     """One GPU behind the C ABI of include/mrt.h. Replaces render() (main.rs:150-295); no CPU fallback."""
 
     OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_POOL_SLOTS, OPT_REFILL_LANES, OPT_FINISH_PATHS = 1, 2, 3, 4, 8
-    OPT_BVH_LEAF_TRIS, OPT_BVH_TRI_COST, OPT_DEVICE_BUILD, OPT_NODE_BURST, OPT_COMM_SPLIT = 9, 10, 11, 12, 13
+    OPT_BVH_LEAF_TRIS, OPT_BVH_TRI_COST, OPT_DEVICE_BUILD, OPT_NODE_BURST, OPT_COMM_SPLIT, OPT_COMM_SCENE = 9, 10, 11, 12, 13, 14
 
     def __init__(self, device=0, stream=None):
         """device: one CUDA device index, or a list of them -- then the handle drives all of them in this process

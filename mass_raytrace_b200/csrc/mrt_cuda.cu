@@ -623,6 +623,9 @@ struct mrt_context {
     void* comm = nullptr;  // ncclComm_t
     int comm_rank = 0, comm_size = 1;
     bool comm_split = true;               // MRT_OPT_COMM_SPLIT
+    bool comm_scene = true;               // MRT_OPT_COMM_SCENE: on a one-process-per-GPU communicator the root's scene is built once and broadcast
+    void* d_scene_hdr = nullptr;          // device + pinned copies of the broadcast header
+    void* h_scene_hdr = nullptr;
     std::vector<mrt_context*> peers;      // devices[1..] of mrt_context_create_multi (owned by this, the leader)
     unsigned long long* d_count = nullptr;  // sample-count cell of the reduce
     unsigned long long* h_count = nullptr;  // pinned
@@ -905,6 +908,8 @@ void mrt_context_destroy(mrt_context* ctx) {
     }
     cudaFree(ctx->d_count);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    cudaFree(ctx->d_scene_hdr);
+    if (ctx->h_scene_hdr) cudaFreeHost(ctx->h_scene_hdr);
     free_scene(ctx);
     release_scene_arena(ctx);
     free_pool(ctx);
@@ -994,10 +999,20 @@ constexpr size_t kDeviceTlasMin = 1u << 20;  // an LBVH over instances traverses
 
 static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device);
 
+static int comm_scene_broadcast(mrt_context* ctx, int root_rc);
+
 int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
     if (!ctx) return MRT_E_INVALID;
-    int rc = scene_upload_impl(ctx, s, ctx->opt_device_build != 0);
-    if (rc == kRetryOnHost) rc = scene_upload_impl(ctx, s, false);
+    // One process per GPU: the scene is the same on every rank (it is replicated, never sharded), so only the root validates, builds
+    // and uploads it; the finished device arrays then travel over NVLink (one grouped ncclBroadcast) instead of N times over PCIe
+    // from N host copies. COLLECTIVE like mrt_render on such a context; the other ranks' `s` is not read and may be NULL.
+    const bool collective = ctx->comm_size > 1 && ctx->peers.empty() && ctx->comm_scene;
+    int rc = MRT_OK;
+    if (!collective || ctx->comm_rank == 0) {
+        rc = scene_upload_impl(ctx, s, ctx->opt_device_build != 0);
+        if (rc == kRetryOnHost) rc = scene_upload_impl(ctx, s, false);
+    }
+    if (collective) return comm_scene_broadcast(ctx, rc);
     if (rc) return rc;
     for (mrt_context* p : ctx->peers)
         if ((rc = replicate_scene(ctx, p))) return fail(ctx, rc, "device " + std::to_string(p->device) + ": " + p->err);
@@ -1808,6 +1823,7 @@ int mrt_set_option(mrt_context* ctx, int option, uint64_t value) {
 static int set_option_one(mrt_context* ctx, int option, uint64_t value) {
     switch (option) {
         case MRT_OPT_COMM_SPLIT: ctx->comm_split = value != 0; return MRT_OK;
+        case MRT_OPT_COMM_SCENE: ctx->comm_scene = value != 0; return MRT_OK;
         case MRT_OPT_COUNT_VISITS: ctx->opt_count = value != 0; return MRT_OK;
         case MRT_OPT_TIME_KERNELS: ctx->opt_time = value != 0; return MRT_OK;
         case MRT_OPT_POOL_SLOTS:
@@ -2010,6 +2026,99 @@ static int comm_reduce(mrt_context* ctx) {
 int mrt_comm_reduce(mrt_context* ctx) {
     if (!ctx) return MRT_E_INVALID;
     return comm_reduce(ctx);
+}
+
+// The root's finished scene to every member of a one-process-per-GPU communicator. A fixed-size header goes first (the root's
+// upload status, so that a failed upload fails everywhere instead of hanging the others; the arena's array sizes and device
+// addresses; DScene and the few host-side facts derived at upload), then every arena array, all in one NCCL group on the render
+// streams. The receivers rebase DScene's pointers from the root's addresses to their own.
+namespace {
+constexpr size_t kMaxSceneBufs = 24;
+struct SceneHeader {
+    int32_t rc;
+    uint32_t n_bufs;
+    uint32_t auto_refill_lanes, auto_node_burst, material_kinds, pad;
+    uint64_t scene_bytes;
+    uint64_t buf_addr[kMaxSceneBufs], buf_used[kMaxSceneBufs];
+    DScene scene;
+};
+}  // namespace
+static int comm_scene_broadcast(mrt_context* ctx, int root_rc) {
+    std::string why;
+    NcclApi* api = nccl_api(why);
+    if (!api) return fail(ctx, MRT_E_UNSUPPORTED, why);
+    MRT_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->d_scene_hdr) {
+        MRT_CUDA(cudaMalloc(&ctx->d_scene_hdr, sizeof(SceneHeader)));
+        MRT_CUDA(cudaMallocHost(&ctx->h_scene_hdr, sizeof(SceneHeader)));
+    }
+    SceneHeader* h = static_cast<SceneHeader*>(ctx->h_scene_hdr);
+    ncclComm_t comm = static_cast<ncclComm_t>(ctx->comm);
+    const bool root = ctx->comm_rank == 0;
+    if (root) {
+        std::memset(h, 0, sizeof *h);
+        h->rc = root_rc;
+        if (!root_rc && ctx->scene_buf_next > kMaxSceneBufs) h->rc = MRT_E_UNSUPPORTED;
+        if (!h->rc) {
+            h->n_bufs = (uint32_t)ctx->scene_buf_next;
+            for (size_t k = 0; k < ctx->scene_buf_next; ++k) {
+                h->buf_addr[k] = reinterpret_cast<uint64_t>(ctx->scene_bufs[k].p);
+                h->buf_used[k] = ctx->scene_bufs[k].used;
+            }
+            h->auto_refill_lanes = ctx->auto_refill_lanes;
+            h->auto_node_burst = ctx->auto_node_burst;
+            h->material_kinds = ctx->material_kinds;
+            h->scene_bytes = ctx->scene_bytes;
+            h->scene = ctx->scene;
+        }
+        MRT_CUDA(cudaMemcpyAsync(ctx->d_scene_hdr, h, sizeof *h, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+        free_scene(ctx);
+    }
+    ncclResult_t r = api->Broadcast(ctx->d_scene_hdr, ctx->d_scene_hdr, sizeof(SceneHeader), ncclUint8, 0, comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, api, "ncclBroadcast", r);
+    if (!root) {
+        MRT_CUDA(cudaMemcpyAsync(h, ctx->d_scene_hdr, sizeof *h, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (h->rc) {
+        if (root) return h->rc;  // (ctx->err was set by the upload)
+        return fail(ctx, h->rc, "the root rank's mrt_scene_upload failed");
+    }
+    std::vector<void*> mine(h->n_bufs);
+    for (uint32_t k = 0; k < h->n_bufs; ++k) {
+        if (root) { mine[k] = ctx->scene_bufs[k].p; continue; }
+        int rc = arena_alloc(ctx, (size_t)h->buf_used[k], &mine[k]);
+        if (rc) return rc;  // (the other ranks then wait in the broadcast below: an allocation failure here is fatal for the job anyway)
+    }
+    if ((r = api->GroupStart()) != ncclSuccess) return nccl_fail(ctx, api, "ncclGroupStart", r);
+    for (uint32_t k = 0; k < h->n_bufs && r == ncclSuccess; ++k) r = api->Broadcast(mine[k], mine[k], (size_t)h->buf_used[k], ncclUint8, 0, comm, ctx->stream);
+    ncclResult_t r2 = api->GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(ctx, api, "ncclBroadcast", r);
+    if (r2 != ncclSuccess) return nccl_fail(ctx, api, "ncclGroupEnd", r2);
+    if (!root) {
+        DScene d = h->scene;
+        auto rebase = [&](auto*& ptr) {
+            if (!ptr) return;
+            const uint64_t q = reinterpret_cast<uint64_t>(ptr);
+            for (uint32_t k = 0; k < h->n_bufs; ++k)
+                if (q >= h->buf_addr[k] && q < h->buf_addr[k] + std::max<uint64_t>(h->buf_used[k], 1)) {
+                    ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(static_cast<char*>(mine[k]) + (q - h->buf_addr[k]));
+                    return;
+                }
+        };
+        rebase(d.nodes); rebase(d.spheres); rebase(d.sphere_aux); rebase(d.tri_verts); rebase(d.tri_map); rebase(d.tri_shading);
+        rebase(d.instances); rebase(d.blas); rebase(d.volumes); rebase(d.materials); rebase(d.surfaces); rebase(d.textures); rebase(d.texels);
+        ctx->scene = d;
+        ctx->has_scene = true;
+        ctx->auto_refill_lanes = h->auto_refill_lanes;
+        ctx->auto_node_burst = h->auto_node_burst;
+        ctx->material_kinds = h->material_kinds;
+        ctx->scene_bytes = h->scene_bytes;
+    }
+    MRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MRT_OK;
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------------------------
