@@ -315,7 +315,7 @@ enum {
     MRT_OPT_BVH_TRI_COST = 10, /* SAH rebuild: cost of one triangle test in hundredths of a node visit (default 100) */
     MRT_OPT_COMM_SPLIT = 13,   /* 1 (default): on a context with a communicator mrt_render_accumulate splits the sample range and merges; 0: it renders
                                   the range it is given, locally, and the host calls mrt_comm_reduce */
-    MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 65536, 0 = off) */
+    MRT_OPT_FINISH_PATHS = 8   /* drain: once no samples are left and at most this many paths are alive, one kernel runs them to the end (default 98304, 0 = off) */
 };
 int mrt_set_option(mrt_context* ctx, int option, uint64_t value);
 int mrt_get_stats(mrt_context* ctx, mrt_stats* out);

@@ -607,7 +607,7 @@ struct mrt_context {
     // options
     bool opt_count = false, opt_time = false;
     uint64_t opt_pool_slots = 0;
-    uint32_t opt_finish_paths = 65536;
+    uint32_t opt_finish_paths = 98304;  // 64 K / 96 K / 128 K / 256 K measured (profiles/r02_drain_cost.txt): 96 K is best or equal on every workload
     uint32_t opt_leaf_tris = 4, opt_tri_cost = 100;
     uint32_t opt_device_build = 1;  // MRT_OPT_DEVICE_BUILD: 0 host SAH everywhere; 1 GPU LBVH for big meshes (and for a TLAS of >= 2^20 objects);
                                     // 2 also for a TLAS of >= 16384 objects
@@ -1686,9 +1686,10 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
             if (ctx->opt_time)
                 for (int k = 0; k < 6; ++k) { MRT_CUDA(cudaEventCreate(&e[k])); tev.push_back(e[k]); }
             if (rp.finish_paths) {
-                if (mode == 2) k_finish<true, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
-                else if (mode == 1) k_finish<false, true><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
-                else k_finish<false, false><<<512, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                const unsigned gf = std::max(512u, (rp.finish_paths + 127u) / 128u);  // one thread per path at the threshold
+                if (mode == 2) k_finish<true, true><<<gf, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                else if (mode == 1) k_finish<false, true><<<gf, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
+                else k_finish<false, false><<<gf, 128, 0, ctx->stream>>>(ctx->scene, rp, pool, ctx->d_q, cur, ctx->d_accum, ctx->d_nonfinite);
                 st.kernel_launches++;
             }
             if (ctx->opt_time) MRT_CUDA(cudaEventRecord(e[0], ctx->stream));
@@ -2072,9 +2073,6 @@ static int comm_scene_broadcast(mrt_context* ctx, int root_rc) {
             h->scene = ctx->scene;
         }
         MRT_CUDA(cudaMemcpyAsync(ctx->d_scene_hdr, h, sizeof *h, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        cudaStreamSynchronize(ctx->stream);
-        free_scene(ctx);
     }
     ncclResult_t r = api->Broadcast(ctx->d_scene_hdr, ctx->d_scene_hdr, sizeof(SceneHeader), ncclUint8, 0, comm, ctx->stream);
     if (r != ncclSuccess) return nccl_fail(ctx, api, "ncclBroadcast", r);
@@ -2084,8 +2082,9 @@ static int comm_scene_broadcast(mrt_context* ctx, int root_rc) {
     }
     if (h->rc) {
         if (root) return h->rc;  // (ctx->err was set by the upload)
-        return fail(ctx, h->rc, "the root rank's mrt_scene_upload failed");
+        return fail(ctx, h->rc, "the root rank's mrt_scene_upload failed");  // (this rank keeps the scene it had, like the root)
     }
+    if (!root) free_scene(ctx);  // (the stream was synchronised above: nothing reads the old arrays any more)
     std::vector<void*> mine(h->n_bufs);
     for (uint32_t k = 0; k < h->n_bufs; ++k) {
         if (root) { mine[k] = ctx->scene_bufs[k].p; continue; }

@@ -122,3 +122,27 @@ def test_c_host_on_two_gpus_writes_the_same_image(tmp_path):
         assert p.returncode == 0, p.stderr
         outs.append(p.stdout.split()[-1])  # fnv1a of the rgb8 image
     assert outs[0] == outs[1]
+
+
+def test_one_process_per_gpu_collective_upload_and_render(renderer, tmp_path):
+    """torchrun-style hosts: one context per process joined by mrt_comm_init_rank. mrt_scene_upload is collective there (rank 0 builds
+    and uploads, ncclBroadcast over NVLink, the other ranks pass NULL), mrt_render splits and merges; rank 0's image must be the
+    single-GPU image byte for byte, and a scene the root rejects must fail on every rank."""
+    import hashlib
+    import sys
+
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out, mesh = str(tmp_path / "out"), str(tmp_path / "m.ply")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(ROOT, "tests", "multi_process_child.py"), out, mesh], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    got = dict((ln.split()[0], ln.split()[1:]) for ln in open(out + ".0").read().splitlines())
+    n, md = scenes.write_synthetic_ply(mesh, 256, 128, seed=4)
+    for name, (w, c), W, H, spp in (("cornell", scenes.cornell_box(1.0), 96, 96, 13), ("mesh", scenes.lucy_layout(mesh, md, grid=0), 160, 90, 5)):
+        renderer.set_scene(NativeScene(w, c))
+        rgb, b, cnt = renderer.render(W, H, spp, 50, seed=11)
+        assert got[name][0] == hashlib.sha256(rgb.tobytes() + b.tobytes()).hexdigest(), name
+    for rank in (0, 1):
+        rej = [ln for ln in open(f"{out}.{rank}").read().splitlines() if ln.startswith("rejected")][0]
+        assert "abi_version" in rej or "root rank" in rej, rej

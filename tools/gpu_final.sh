@@ -11,7 +11,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 CMD="python bench.py --steps 2 --warmup 3 --spp 32 --no-cpu-baseline --no-per-config --no-parity"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo plain failed; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_mesh1m_spp32.csv $CMD > gpurun_out/${TAG}_ncu_l.log 2>&1
-for spec in "cornell 32 8" "mesh1m 32 5" "mesh10m 4 4" "book2 16 8"; do
+for spec in "cornell 32 8" "mesh1m 32 5" "mesh10m 4 4" "book2 32 3"; do
   set -- $spec
   C="python tools/gpu_one_render.py $1 $2"
   $C > gpurun_out/${TAG}_plain_$1.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_extend --launch-skip $3 --launch-count 1 -o gpurun_out/${TAG}_extend_$1 -f $C > gpurun_out/${TAG}_ncu_$1.log 2>&1
@@ -20,7 +20,7 @@ done
 C="python tools/gpu_one_render.py cornell 32"
 ncu --set full --clock-control none --import-source on -k regex:k_shade --launch-skip 8 --launch-count 1 -o gpurun_out/${TAG}_shade_cornell -f $C > gpurun_out/${TAG}_ncu_s.log 2>&1
 ncu -i gpurun_out/${TAG}_shade_cornell.ncu-rep --page raw --csv > gpurun_out/${TAG}_shade_cornell_raw.csv 2>/dev/null
-python - <<'PY'
+TAG=$TAG python - <<'PY'
 import json,glob,os
 TAG=os.environ.get("TAG","")
 for f in sorted(glob.glob("gpurun_out/*_bench_*.json")):

@@ -21,7 +21,7 @@ for k in np.argsort(-times)[:3]:
     rgb, b, cnt = r.download()
     print(f"sample {s}: {times[k]:.2f} ms, rays {st['rays']}, node visits/ray {st['node_visits'] / st['rays']:.1f}, tri tests/ray {st['tri_tests'] / st['rays']:.1f}, "
           f"non-finite pixels {int((~np.isfinite(rgb)).any(-1).sum())}, max bounces {int(b.max())} at pixel {np.unravel_index(int(b.argmax()), b.shape)}")
-    r.set_option(Renderer.OPT_FINISH_PATHS, 0); r.reset(W, H); r.accumulate(s, 1, 50, seed=2024); print("   without k_finish:", r.stats()["render_ms"], "ms", r.stats()["iterations"], "iterations"); r.set_option(Renderer.OPT_FINISH_PATHS, 65536)
+    r.set_option(Renderer.OPT_FINISH_PATHS, 0); r.reset(W, H); r.accumulate(s, 1, 50, seed=2024); print("   without k_finish:", r.stats()["render_ms"], "ms", r.stats()["iterations"], "iterations"); r.set_option(Renderer.OPT_FINISH_PATHS, 98304)
 s = lo + int(times.argmax())
 r.set_option(Renderer.OPT_TIME_KERNELS, 1); r.reset(W, H); r.accumulate(s, 1, 50, seed=2024); st = r.stats(); r.set_option(Renderer.OPT_TIME_KERNELS, 0)
 print("timed:", {k: st[k] for k in ("render_ms", "extend_ms", "shade_ms", "generate_ms", "iterations", "kernel_launches")})
