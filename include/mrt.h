@@ -223,6 +223,7 @@ typedef struct mrt_stats {
     uint64_t scene_bytes;     /* device bytes of the uploaded scene */
     uint64_t pool_slots;      /* paths in flight (entries per ray queue) */
     uint64_t node_bytes;      /* bytes of one inner-node record of the uploaded acceleration structure (what one node visit fetches) */
+    uint64_t max_ray_node_visits; /* most node visits any single ray made (instrumented renders): a ray that defeats the box tests shows here */
 } mrt_stats;
 
 typedef struct mrt_context mrt_context;

@@ -50,7 +50,7 @@ class mrt_stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("instance_tests", C.c_uint64), ("volume_tests", C.c_uint64), ("iterations", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_float), ("extend_ms", C.c_float), ("shade_ms", C.c_float), ("generate_ms", C.c_float),
-                ("scene_bytes", C.c_uint64), ("pool_slots", C.c_uint64), ("node_bytes", C.c_uint64)]
+                ("scene_bytes", C.c_uint64), ("pool_slots", C.c_uint64), ("node_bytes", C.c_uint64), ("max_ray_node_visits", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

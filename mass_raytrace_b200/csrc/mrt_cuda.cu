@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
     const uint32_t n_cont = q->n_cont;
     uint32_t refill_lanes = rp.refill_lanes;
     const uint32_t node_burst = rp.node_burst;
-    VisitCounters cnt{0, 0, 0, 0, 0};
+    VisitCounters cnt{0, 0, 0, 0, 0, 0};
     unsigned long long ray_start = 0;  // (COUNT) node visits when the lane's current ray began
     (void)ray_start;
     uint32_t stack[kStackSize];
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
             HitRec h = T.best;
             int32_t m = -1;
             if (pending) {
+                if (COUNT) cnt.max_ray_nodes = max(cnt.max_ray_nodes, cnt.node_visits - ray_start);
 #ifdef MRT_TRACE_MONSTERS
                 if (COUNT && cnt.node_visits - ray_start > 100000ull)
                     printf("monster ray: %llu node visits, pixel %u sample %u bounce %u o (%.9g %.9g %.9g) d (%.9g %.9g %.9g) hit t %.9g prim %08x\n", cnt.node_visits - ray_start,
@@ -311,6 +312,9 @@ __global__ void __launch_bounds__(kExtendThreads, COUNT || ALPHA ? 1 : (VOLUME ?
             for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
             if (lane == 0 && x) atomicAdd(&dst[k], x);
         }
+        unsigned long long mx = cnt.max_ray_nodes;
+        for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, off));
+        if (lane == 0 && mx) atomicMax(&q->visits.max_ray_nodes, mx);
     }
 }
 
@@ -1653,6 +1657,7 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
     mrt_stats& st = ctx->stats;
     st.paths = total; st.rays = 0; st.node_visits = st.tri_tests = st.sphere_tests = st.instance_tests = st.volume_tests = 0;
     st.iterations = st.extend_launches = st.kernel_launches = 0;
+    st.max_ray_node_visits = 0;
     st.render_ms = st.extend_ms = st.shade_ms = st.generate_ms = 0.0f;
     st.scene_bytes = ctx->scene_bytes;
     st.node_bytes = sizeof(DNode);
@@ -1742,6 +1747,7 @@ static int render_accumulate_local(mrt_context* ctx, uint32_t spp_begin, uint32_
     st.sphere_tests = fin.visits.sphere_tests;
     st.instance_tests = fin.visits.instance_tests;
     st.volume_tests = fin.visits.volume_tests;
+    st.max_ray_node_visits = fin.visits.max_ray_nodes;
     if (ctx->opt_time) {
         for (size_t i = 0; i + 5 < tev.size(); i += 6) {
             float ms = 0;
@@ -1865,6 +1871,7 @@ int mrt_get_stats(mrt_context* ctx, mrt_stats* out) {
         out->sphere_tests += q.sphere_tests; out->instance_tests += q.instance_tests; out->volume_tests += q.volume_tests;
         out->extend_launches += q.extend_launches; out->kernel_launches += q.kernel_launches;
         out->iterations = std::max(out->iterations, q.iterations);
+        out->max_ray_node_visits = std::max(out->max_ray_node_visits, q.max_ray_node_visits);
         out->render_ms = std::max(out->render_ms, q.render_ms); out->extend_ms = std::max(out->extend_ms, q.extend_ms);
         out->shade_ms = std::max(out->shade_ms, q.shade_ms); out->generate_ms = std::max(out->generate_ms, q.generate_ms);
     }

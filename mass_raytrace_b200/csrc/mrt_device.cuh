@@ -71,6 +71,7 @@ struct DCamera {
 
 struct VisitCounters {
     unsigned long long node_visits, tri_tests, sphere_tests, instance_tests, volume_tests;
+    unsigned long long max_ray_nodes;  // most node visits of one ray
 };
 
 // ---- f32 vector helpers in the reference's operation order (math/generic.rs) ---------------------------------

@@ -173,6 +173,25 @@ def test_aov_axis_parallel_rays(renderer):
             assert np.isfinite(g["t"][127]).mean() > 0.5
 
 
+def test_no_ray_defeats_the_box_tests(renderer, mesh_ply):
+    """The performance face of the axis-parallel fix: a ray with zero direction components (here every primary ray of the centre row
+    and column of an axis-aligned camera, and Lambertian bounces that fall back to an axis-aligned normal, material.rs:207) must be
+    culled like any other. When such rays ignored an axis instead, one of them visited 250,000 nodes of a 1 M-triangle mesh;
+    mrt_stats.max_ray_node_visits (instrumented renders) bounds the worst ray of a render."""
+    path, md, n = mesh_ply
+    world, _ = scenes.lucy_layout(path, md, grid=1)  # nine instances of a 65k-triangle mesh over a ground cube
+    for cam in (Camera(40.0, V3(0, 1, 12), V3(0, 1, 0), V3(0, 1, 0), 1.0, 0.0, 12.0), Camera(40.0, V3(0, 30, 0), V3(0, 0, 0), V3(0, 0, -1), 1.0, 0.0, 30.0)):
+        renderer.set_scene(NativeScene(world, cam))
+        renderer.set_option(renderer.OPT_COUNT_VISITS, 1)
+        try:
+            renderer.render(255, 255, 16, 50, seed=21)
+            st = renderer.stats()
+        finally:
+            renderer.set_option(renderer.OPT_COUNT_VISITS, 0)
+        assert st["node_visits"] / st["rays"] < 40
+        assert 0 < st["max_ray_node_visits"] < 3000, st["max_ray_node_visits"]  # a whole-tree walk would be ~130,000
+
+
 def test_volume_hit_probability_per_pixel(renderer):
     """Volume::intersect draws its free-flight distance from the path's RNG (geom.rs:638), so a primary ray through a medium
     reports the Volume with probability 1 - exp(-density * chord) and otherwise whatever lies behind. Over 64 seeds the PER-PIXEL hit
