@@ -16,11 +16,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from mass_raytrace_b200 import scenes  # noqa: E402
 from oracle_backend import OracleScene  # noqa: E402
+from extra_scenes import eve_scene, mesh_media_scene  # noqa: E402
 
 SPECS = {
     # name: (scene factory, aov size, render size, spp, seed)
     "cornell": (lambda: scenes.cornell_box(1.0), (64, 64), (48, 48), 64, 2024),
     "book1": (lambda: scenes.book1_spheres(1.5, aperture=0.0), (96, 64), (60, 40), 64, 2024),
+    # round 2: EveMaterial (tangent-space normals through Material::normal, geom.rs:551-560) and media that fill meshes (Volume<I>, geom.rs:595)
+    "eve": (eve_scene, (96, 64), (60, 40), 64, 2024),
+    "mesh_media": (lambda: mesh_media_scene(0.9), (96, 64), (60, 40), 64, 2024),
 }
 
 

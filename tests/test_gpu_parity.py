@@ -14,6 +14,7 @@ from mass_raytrace_b200 import (BLEND_ADDITION, WRAP_CLAMP, WRAP_REPEAT, EveMate
                                 Volume, World, YCbCrTexture, scenes)
 from mass_raytrace_b200.api import Volume as VolumeT
 from oracle_backend import OracleScene
+from extra_scenes import eve_scene, mesh_media_scene
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -553,19 +554,8 @@ def test_volume_over_model_and_instance_targets(renderer):
     rotated, scaled Instance of the cube. Dense media: the primary ray scatters right behind the surface it enters through; media of
     moderate density: per-pixel hit frequencies over 48 seeds agree with the oracle's like two samples of one probability; converged
     renders agree statistically."""
-    from mass_raytrace_b200 import PlyLoader
-    cam = Camera(30.0, V3(0, 1.2, 7), V3(0, 0.9, 0), V3(0, 1, 0), 1.5, 0.0, 7.0)
-
-    def build(density):
-        w = World(SolidBackground(V3(0.9, 0.95, 1.0)))
-        w.add(Sphere(Lambertian(SolidColor((0.5, 0.5, 0.5, 1))), V3(0, -1000, 0), 1000.0))
-        ball = Model(scenes.uv_sphere_triangles((-1.3, 1.0, 0.0), 0.9, 24, 12, material=()))
-        w.add(Volume(ball, density, V3(0.8, 0.3, 0.2)))
-        cube = Model(PlyLoader.load(scenes.CUBE_PLY))
-        w.add(Volume(cube.instance(V3(1.3, 0.9, 0.0), V3(0.3, 0.6, 0.1), V3(0.8, 0.8, 0.8)), density, V3(0.2, 0.4, 0.8)))
-        w.add(Sphere(Metal(0.0, SolidColor((0.9, 0.9, 0.9, 1))), V3(0, 0.5, -2.5), 0.5))
-        w.build_bvh()
-        return w
+    build = lambda density: mesh_media_scene(density)[0]
+    cam = mesh_media_scene(1.0)[1]
 
     W, H = 150, 100
     # dense: the hit is the Volume, t just behind the entry surface, normal (1, 0, 0) (geom.rs:644-651)
@@ -604,29 +594,6 @@ def test_volume_over_model_and_instance_targets(renderer):
     stat_compare(renderer, w, cam, 72, 48, 96)
 
 
-def eve_scene(seed=7, flat_normals=False):
-    """UV meshes carrying an EveMaterial (eve.rs:23-133): normal + occlusion, albedo + roughness and paint / material / dirt / glow
-    textures, tangent-space normals through Material::normal (geom.rs:551-560)."""
-    rs = np.random.RandomState(seed)
-    no = rs.randint(64, 192, (16, 32, 4)).astype(np.uint8)  # normal x in G, y in A (normal_occlusion :66-73); moderate tilts
-    if flat_normals:
-        no[..., 1] = 128
-        no[..., 3] = 128
-    ar = rs.randint(40, 256, (8, 16, 4)).astype(np.uint8)
-    pmdg = rs.randint(0, 256, (8, 8, 4)).astype(np.uint8)
-    pmdg[..., 2] //= 3       # little dirt
-    pmdg[..., 3] //= 8       # faint glow
-    eve = EveMaterial(Texture(no, WRAP_REPEAT), Texture(ar, WRAP_REPEAT), Texture(pmdg, WRAP_REPEAT))
-    w = World(SkyBackground())
-    w.add(Sphere(Lambertian(SolidColor((0.5, 0.5, 0.5, 1))), V3(0, -1000, 0), 1000.0))
-    w.add(Model(scenes.uv_sphere_triangles((-1.1, 1.0, 0.0), 1.0, 32, 16, material=eve)))
-    ship = Model(scenes.uv_sphere_triangles((0.0, 0.0, 0.0), 1.0, 24, 12, material=eve))
-    w.add(ship.instance(V3(1.2, 0.8, 0.3), V3(0.2, 0.7, 0.1), V3(0.9, 0.6, 0.7)))
-    w.build_bvh()
-    cam = Camera(35.0, V3(0, 2.0, 7), V3(0, 0.9, 0), V3(0, 1, 0), 1.5, 0.0, 7.0)
-    return w, cam
-
-
 def test_eve_material_tangent_space_normals(renderer):
     w, cam = eve_scene()
     renderer.set_scene(NativeScene(w, cam))
@@ -647,6 +614,21 @@ def test_eve_material_tangent_space_normals(renderer):
     stat_compare(renderer, w, cam, 90, 60, 128)
     r = renderer.render(90, 60, 64, 50, seed=3)
     assert renderer.stats()["rays"] > 90 * 60 * 64 * 1.5
+
+
+@pytest.mark.parametrize("name", ["eve", "mesh_media"])
+def test_round2_scenes_vs_golden(renderer, name):
+    """The committed fixtures of the two round-2 features (tests/golden/make_golden.py): primary rays outside the media bit for bit,
+    the converged render against the fixture as one of the two oracle images."""
+    gold = np.load(os.path.join(HERE, "golden", f"{name}.npz"))
+    world, camera = eve_scene() if name == "eve" else mesh_media_scene(0.9)
+    renderer.set_scene(NativeScene(world, camera))
+    h, w = gold["aov_object"].shape
+    g = renderer.render_aov(w, h, seed=int(gold["seed"]))
+    o = dict(object=gold["aov_object"], tri=gold["aov_tri"], t=gold["aov_t"], normal=gold["aov_normal"], albedo=gold["aov_albedo"])
+    check_aov(g, o, exclude=volume_mask(world, g, o), albedo_exact=False)
+    h, w = gold["sum_bounces"].shape
+    stat_compare(renderer, world, camera, w, h, int(gold["spp"]), oracle_a=(gold["sum_rgb"], gold["sum_bounces"]), seed=int(gold["seed"]))
 
 
 def test_resolve_rgb8_matches_reference_tonemap(renderer, oracle):

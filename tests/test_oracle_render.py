@@ -20,7 +20,7 @@ def _golden_make():
     return m
 
 
-@pytest.mark.parametrize("name", ["cornell", "book1"])
+@pytest.mark.parametrize("name", ["cornell", "book1", "eve", "mesh_media"])
 def test_oracle_reproduces_golden(name):
     got = _golden_make().make(name)
     want = np.load(os.path.join(HERE, "golden", f"{name}.npz"))
