@@ -441,9 +441,15 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DScene s
     const RayRec* __restrict__ queue = pool.q_ext[cur];
     const float inf = __int_as_float(0x7f800000);
     unsigned long long rays = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // Consecutive threads take queue entries n / 32 apart: neighbouring entries were shaded together and tend to be paths of one kind --
+    // the ones that stay inside a mesh for all max_depth bounces sit next to each other, and a warp that took 32 of them would run
+    // every one of their bounces with 32 diverged lanes.
+    const uint32_t stride = (n + 31u) / 32u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 32u * stride; i += gridDim.x * blockDim.x) {
+        const uint32_t item = (i & 31u) * stride + (i >> 5);
+        if (item >= n) continue;
         HitEntry e;
-        e.ray = queue[i];
+        e.ray = queue[item];
         bool cont = true;
         while (cont) {
             const float4 o = e.ray.o, d = e.ray.d;
