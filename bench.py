@@ -453,7 +453,7 @@ def main():
         spp = args.spp or spp_default
         line = {
             "metric": "Mpaths/s", "value": main_rec["value"], "unit": "Mpaths/s", "mrays_per_s": main_rec["mrays_per_s"], "n_gpus": world_size, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": main_rec["ms_per_step"], "steps_ms": main_rec["steps_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "spp_per_step": spp, "max_depth": 50,
                        "partition": (f"the {spp} samples of every pixel split over {world_size} ranks (mrt_sample_range), one NCCL int64 sum-reduce per step inside "
