@@ -131,3 +131,40 @@ def test_volume_over_a_mesh_target():
     w.build_bvh()
     a = OracleScene(w, inside).render_aov(17, 17)
     assert (a["object"] == 0).all() and (a["t"] < 0.5).all() and (a["t"] >= 0).all(), (a["t"].min(), a["t"].max())
+
+
+def test_host_flattens_the_round2_scenes():
+    """libmrt_host.so on the scenes of the two round-2 features: an EveMaterial becomes one MRT_MAT_EVE entry whose palette is four
+    consecutive solid surfaces (include/mrt.h), a Volume over a mesh an instance entry that is not in the world list."""
+    import ctypes as C
+
+    from extra_scenes import eve_scene, mesh_media_scene
+    from mass_raytrace_b200 import NativeScene, _ffi
+
+    class M(C.Structure):
+        _fields_ = [("kind", C.c_int32), ("surface", C.c_int32), ("left", C.c_int32), ("right", C.c_int32), ("p", C.c_float * 4)]
+
+    class S(C.Structure):
+        _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("mode", C.c_int32), ("color", C.c_float * 4)]
+
+    class V(C.Structure):
+        _fields_ = [("target", C.c_uint32), ("neg_inv_density", C.c_float), ("material", C.c_int32), ("object_id", C.c_uint32)]
+
+    host = NativeScene(*eve_scene())
+    d = host.desc().contents
+    mats = C.cast(d.materials, C.POINTER(M))
+    surfs = C.cast(d.surfaces, C.POINTER(S))
+    eve = [mats[i] for i in range(d.n_materials) if mats[i].kind == 8]
+    assert len(eve) == 1
+    m = eve[0]
+    pal = C.cast(C.pointer(C.c_float(m.p[0])), C.POINTER(C.c_int32)).contents.value
+    assert 0 <= pal and pal + 4 <= d.n_surfaces and all(surfs[pal + k].kind == 0 for k in range(4))
+    assert [round(surfs[pal + k].color[3], 3) for k in range(3)] == [0.5, 0.85, 2.0]  # glow rides in the alpha of the first three
+    assert all(surfs[x].kind == 1 for x in (m.surface, m.left, m.right)) and d.n_textures == 3
+    host = NativeScene(*mesh_media_scene(0.9))
+    d = host.desc().contents
+    vols = C.cast(d.volumes, C.POINTER(V))
+    assert d.n_volumes == 2 and d.n_instances == 2 and d.n_objects == 4
+    for k in range(2):
+        assert vols[k].target >> 29 == 3 and (vols[k].target & 0x1FFFFFFF) < d.n_instances  # MRT_PRIM_INSTANCE
+        assert abs(vols[k].neg_inv_density + 1.0 / 0.9) < 1e-6

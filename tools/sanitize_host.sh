@@ -10,7 +10,7 @@ cp mass_raytrace_b200/libmrt_host.so $OUT/libmrt_host.so.orig
 trap 'cp $OUT/libmrt_host.so.orig mass_raytrace_b200/libmrt_host.so; touch mass_raytrace_b200/libmrt_host.so' EXIT
 cp $OUT/libmrt_host.so mass_raytrace_b200/libmrt_host.so
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
-    python -m pytest tests/test_image_export.py tests/test_obj_loader.py tests/test_ply_loader.py tests/test_host_vs_oracle.py tests/test_oracle_kat.py \
+    python -m pytest tests/test_image_export.py tests/test_obj_loader.py tests/test_ply_loader.py tests/test_host_vs_oracle.py tests/test_oracle_kat.py tests/test_oracle_render.py \
     -q -p no:cacheprovider 2>&1 | tee $OUT/host_asan.log | tail -2
 if grep -q "runtime error\|AddressSanitizer" $OUT/host_asan.log; then echo "sanitizer reports in $OUT/host_asan.log"; exit 1; fi
 for san in address,undefined thread; do
