@@ -176,7 +176,9 @@ def run_reference(args):
         "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "mrays_per_s": rays / total / 1e6, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "max_depth": 50},
+        "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "spp_per_step": args.spp or spp, "max_depth": 50,
+                   "cpu_thread_policy": "max(host cores - 2, 1) (main.rs:159-160) for cpu_baseline and --impl reference alike",
+                   "sample": "each step renders a bounded sample of this workload (cpu_baseline.sample); the value is the normalised rate"},
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": threads, "host_cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
