@@ -460,7 +460,7 @@ def main():
             "config": {"workload": f"configs[{cfg}]: {desc}", "name": args.workload, "width": w, "height": h, "spp_per_step": spp, "max_depth": 50,
                        "partition": (f"the {spp} samples of every pixel split over {world_size} ranks (mrt_sample_range), one NCCL int64 sum-reduce per step inside "
                                      f"the library" if world_size > 1 else "single GPU"),
-                       "l2": "flushed between steps (256 MiB write); the ray / shade queues of one iteration (1.8 GB at 16M paths in flight) also exceed the 126 MB L2",
+                       "l2": "flushed between steps (256 MiB write); the ray / shade queues of one iteration (3.6 GB at 32M paths in flight) also exceed the 126 MB L2",
                        "scene_build_s": main_rec["scene_build_s"], "host_mesh_bvh": "deferred (mrth_defer_mesh_bvh)", "rays_per_path": main_rec["rays_per_path"],
                        "bvh": "host SAH for every mesh" if args.bvh == "sah" else "GPU-built for meshes of >= 16384 triangles, host SAH otherwise",
                        "cpu_thread_policy": "max(host cores - 2, 1) (main.rs:159-160) for cpu_baseline and --impl reference alike"},

@@ -300,7 +300,7 @@ enum { MRT_DISPLAY_DEFAULT = 0, MRT_DISPLAY_DENOISE = 1, MRT_DISPLAY_DEPTH = 2, 
 enum {
     MRT_OPT_COUNT_VISITS = 1, /* count node / primitive visits in the next renders (instrumented kernel) */
     MRT_OPT_TIME_KERNELS = 2, /* CUDA-event time of every generate / extend / shade launch */
-    MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^26 (0 = default 2^24; 96 B + 64 B per material kind in the scene each) */
+    MRT_OPT_POOL_SLOTS = 3,   /* paths in flight = entries per ray queue, 1024 .. 2^26 (0 = default 2^25, clamped to the size of the job; 96 B + 64 B per material kind in the scene each) */
     MRT_OPT_REFILL_LANES = 4, /* k_extend: commit and refill finished lanes of continuing rays once this many of a warp's 32 lanes are idle;
                                  0 (default) = by scene: 32 (whole batches), or 12 when a mesh's tree is deep */
     MRT_OPT_DEVICE_BUILD = 11, /* mrt_scene_upload builds trees ON THE GPU (linear BVH, ~3 ms per million primitives): 1 (default) the BLAS of meshes

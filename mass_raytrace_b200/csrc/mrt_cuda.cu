@@ -1604,7 +1604,8 @@ static uint32_t shade_regions(const mrt_context* ctx, uint8_t region[Q_COUNT + 3
 }
 
 static int ensure_pool(mrt_context* ctx, uint64_t total_work, uint32_t regions) {
-    uint64_t want = ctx->opt_pool_slots ? ctx->opt_pool_slots : (1ull << 24);  // measured: 16 M rays in flight beat 4 M by 4 % (Cornell) to 26 % (1 M-triangle mesh)
+    // measured: 16 M rays in flight beat 4 M by 4 % (Cornell) to 26 % (1 M-triangle mesh), 32 M beat 16 M by another 0.4 % to 3 % (profiles/README.md)
+    uint64_t want = ctx->opt_pool_slots ? ctx->opt_pool_slots : (1ull << 25);
     want = std::min<uint64_t>(want, std::max<uint64_t>((total_work + 1023) / 1024 * 1024, 1024));
     want = std::min<uint64_t>(want, 1ull << 26);
     if (ctx->pool.capacity == want && ctx->pool.regions >= regions) return MRT_OK;

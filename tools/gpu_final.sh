@@ -11,6 +11,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 CMD="python bench.py --steps 2 --warmup 3 --spp 32 --no-cpu-baseline --no-per-config --no-parity"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo plain failed; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_mesh1m_spp32.csv $CMD > gpurun_out/${TAG}_ncu_l.log 2>&1
+export MRT_POOL_SLOTS=16777216  # the captures (and tools/ncu_side_files.py) are per launch of 2^24 rays
 for spec in "cornell 32 8" "mesh1m 32 5" "mesh10m 4 4" "book2 32 3"; do
   set -- $spec
   C="python tools/gpu_one_render.py $1 $2"

@@ -17,7 +17,9 @@ elif name == "mesh10m":
     for i in range(10):
         p = os.path.join(tmp, f"m{i}.ply"); n, md = scenes.write_synthetic_ply(p, 1024, 512, seed=100 + i); paths.append(p); mds.append(md)
     (w, c), W, H = scenes.multi_mesh(paths, mds), 3840, 2160
-r = Renderer(0); r.set_scene(NativeScene(w, c))
+r = Renderer(0)
+if os.environ.get("MRT_POOL_SLOTS"): r.set_option(Renderer.OPT_POOL_SLOTS, int(os.environ["MRT_POOL_SLOTS"]))  # the ncu captures of profiles/ were taken at 2^24
+r.set_scene(NativeScene(w, c))
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 best = 1e9
 for rep in range(reps):
