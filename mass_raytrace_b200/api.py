@@ -338,7 +338,7 @@ class NativeScene:
 
     def _check(self, rc, what):
         if rc < 0:
-            raise RuntimeError(f"{what}: {self._fn('last_error')(self._h).decode()}")
+            raise RuntimeError(f"{what}: {self._fn('last_error')(self._h).decode(errors="replace")}")
         return rc
 
     def close(self):
@@ -557,7 +557,7 @@ class Renderer:
             rc = self.lib.mrt_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
             what = f"mrt_context_create({device})"
         if rc != 0:
-            raise MrtError(f"{what} = {rc}: {self.lib.mrt_last_error(None).decode()}")
+            raise MrtError(f"{what} = {rc}: {self.lib.mrt_last_error(None).decode(errors="replace")}")
         self._h = h
         self.size = None
         self._scene_keepalive = None
@@ -569,7 +569,7 @@ class Renderer:
         lib = _ffi.cuda_lib()
         rc = lib.mrt_comm_unique_id(buf)
         if rc != 0:
-            raise MrtError(f"mrt_comm_unique_id = {rc}: {lib.mrt_last_error(None).decode()}")
+            raise MrtError(f"mrt_comm_unique_id = {rc}: {lib.mrt_last_error(None).decode(errors="replace")}")
         return bytes(buf)
 
     def comm_init_rank(self, unique_id, rank, n_ranks):
@@ -598,7 +598,7 @@ class Renderer:
 
     def _check(self, rc, what):
         if rc != 0:
-            raise MrtError(f"{what} = {rc}: {self.lib.mrt_last_error(self._h).decode()}")
+            raise MrtError(f"{what} = {rc}: {self.lib.mrt_last_error(self._h).decode(errors="replace")}")
 
     def set_scene(self, scene: NativeScene, keep_topology=False):
         """mrt_scene_upload (+ mrt_camera_set). keep_topology: traverse the caller's BVH as built by BvhNode::new (geom.rs:109-161)

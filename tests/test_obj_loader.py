@@ -230,3 +230,40 @@ def test_png_decoder_survives_corruption(tmp_path):
         except RuntimeError:
             rejected += 1
     assert decoded + rejected == 400 and rejected > 100
+
+
+def test_corrupted_obj_mtl_and_png_never_crash(tmp_path):
+    """Random damage to the .obj, its .mtl and its texture: the host loader returns a mesh or an error (ObjLoader::load returns
+    Result, obj_loader.rs:332), never a crash; tools/sanitize_host.sh runs this under ASan + UBSan."""
+    d = str(tmp_path)
+    path = _write_scene(d)
+    rng = np.random.default_rng(21)
+    files = [path, os.path.join(d, "scene materials.mtl"), os.path.join(d, "tex.png")]
+    good = [open(f, "rb").read() for f in files]
+    loaded = failed = 0
+    for trial in range(240 * int(os.environ.get("MRT_FUZZ_SCALE", "1"))):
+        which = trial % 3
+        b = bytearray(good[which])
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            for i in rng.integers(0, len(b), rng.integers(1, 6)):
+                b[i] = int(rng.integers(0, 256))
+        elif kind == 1:
+            b = b[:int(rng.integers(0, len(b)))]
+        elif kind == 2:
+            i = int(rng.integers(0, len(b))); j = min(len(b), i + int(rng.integers(1, 30)))
+            b = b[:i] + b[j:]
+        else:  # swap two lines (text) / two 8-byte runs (png)
+            i, j = sorted(int(x) for x in rng.integers(0, max(len(b) - 8, 1), 2))
+            b[i:i + 8], b[j:j + 8] = b[j:j + 8], b[i:i + 8]
+        for k, f in enumerate(files):
+            open(f, "wb").write(bytes(b) if k == which else good[k])
+        for builder in (SimpleTexturedBuilder(WRAP_REPEAT), ObjFns(Lambertian(SolidColor((1, 0, 0, 1))))):
+            try:
+                v, nrm, uv, mats = _load(NativeScene, path, builder)
+                assert len(v) >= 1 and len(v) == len(nrm) == len(uv) == len(mats)
+                loaded += 1
+            except RuntimeError as e:
+                assert str(e)
+                failed += 1
+    assert loaded > 20 and failed > 20

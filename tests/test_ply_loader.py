@@ -1,5 +1,6 @@
 """PlyLoader (reference src/ply_loader.rs): the host library's reader and the oracle's restatement on the same files --
 ascii, binary little/big endian, skipped properties and elements, quads silently dropped, header errors."""
+import os
 import struct
 
 import numpy as np
@@ -143,3 +144,65 @@ def test_stl_binary(tmp_path, backend):
     _write_stl(p, [])
     with pytest.raises(RuntimeError):  # Model::new over an empty Vec: BvhNode::new hits unreachable!() (geom.rs:153)
         _load_stl(p, backend)
+
+
+# ---- corrupted files: a loader returns triangles or an error, it never crashes or reads out of bounds -----------------------------
+# (the reference's loaders return Result / panic on bad input; tools/sanitize_host.sh runs this file under ASan + UBSan)
+FUZZ = 150 * int(os.environ.get("MRT_FUZZ_SCALE", "1"))  # tools/sanitize_host.sh can be run with a larger scale
+
+
+def _corruptions(data, rng, n):
+    for _ in range(n):
+        b = bytearray(data)
+        kind = rng.integers(0, 4)
+        if kind == 0:  # flip bytes
+            for i in rng.integers(0, len(b), rng.integers(1, 6)):
+                b[i] = int(rng.integers(0, 256))
+        elif kind == 1:  # truncate
+            b = b[:int(rng.integers(0, len(b)))]
+        elif kind == 2:  # drop a slice from the middle
+            i = int(rng.integers(0, len(b))); j = min(len(b), i + int(rng.integers(1, 40)))
+            b = b[:i] + b[j:]
+        else:  # overwrite a run with 0xFF (huge counts, NaNs, negative indices)
+            i = int(rng.integers(0, len(b))); j = min(len(b), i + int(rng.integers(1, 9)))
+            b[i:j] = b"\xFF" * (j - i)
+        yield bytes(b)
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+def test_corrupted_ply_never_crashes(tmp_path, fmt):
+    src = str(tmp_path / "good.ply")
+    scenes.write_synthetic_ply(src, 6, 4, seed=2, fmt=fmt)
+    data = open(src, "rb").read()
+    rng = np.random.default_rng(11)
+    loaded = failed = 0
+    for k, bad in enumerate(_corruptions(data, rng, FUZZ)):
+        p = str(tmp_path / "bad.ply")
+        open(p, "wb").write(bad)
+        try:
+            v, _ = _load(p, NativeScene)
+            assert v.ndim == 2 and v.shape[1] == 9 and len(v) >= 1
+            loaded += 1
+        except RuntimeError as e:
+            assert str(e)
+            failed += 1
+    assert failed > 20 and loaded + failed == FUZZ  # most corruptions are detected; a flipped coordinate byte still loads
+
+
+def test_corrupted_stl_never_crashes(tmp_path):
+    p = str(tmp_path / "good.stl")
+    tris = np.random.default_rng(5).normal(size=(40, 9)).astype(np.float32).tolist()
+    _write_stl(p, tris, attr_bytes=4)
+    data = open(p, "rb").read()
+    rng = np.random.default_rng(12)
+    loaded = failed = 0
+    for bad in _corruptions(data, rng, FUZZ):
+        open(p, "wb").write(bad)
+        try:
+            v = _load_stl(p, NativeScene)
+            assert v.ndim == 2 and v.shape[1] == 9 and len(v) >= 1
+            loaded += 1
+        except RuntimeError as e:
+            assert str(e)
+            failed += 1
+    assert failed > 20 and loaded + failed == FUZZ
