@@ -16,6 +16,7 @@
  */
 #ifndef MRT_H
 #define MRT_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -266,6 +267,11 @@ int mrt_sample_range(int rank, int size, uint32_t spp_begin, uint32_t spp_count,
 
 /* replaces Arc::new(world) main.rs:157 (after world.build_bvh() main.rs:112): copies the scene to the device once */
 int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* scene);
+/* The checks mrt_scene_upload makes before it touches the device, on their own: no context, no GPU. Returns MRT_OK or the code
+ * the upload would fail with (index ranges of every table, tree shape under MRT_SCENE_KEEP_TOPOLOGY, unsupported features);
+ * the message is copied to why[0 .. why_bytes) when why is not NULL. What Rust's type system guarantees about a World
+ * (world.rs:95-122) and a flattened scene cannot: a host can run it in its own tests without a device. */
+int mrt_scene_validate(const mrt_scene_desc* scene, char* why, size_t why_bytes);
 /* replaces Arc::new(camera) main.rs:158 */
 int mrt_camera_set(mrt_context* ctx, const mrt_camera* camera);
 

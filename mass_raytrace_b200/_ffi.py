@@ -69,6 +69,7 @@ CUDA_API = {
     "mrt_context_destroy": (None, [C.c_void_p]),
     "mrt_last_error": (C.c_char_p, [C.c_void_p]),
     "mrt_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(mrt_scene_desc)]),
+    "mrt_scene_validate": (C.c_int, [C.POINTER(mrt_scene_desc), C.c_char_p, C.c_size_t]),
     "mrt_camera_set": (C.c_int, [C.c_void_p, C.POINTER(mrt_camera)]),
     "mrt_render_aov": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, f32p, f32p, u32p, u32p, f32p]),
     "mrt_render": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, f32p, u32p, u32p]),

@@ -1007,6 +1007,128 @@ constexpr uint32_t kDeviceBuildMin = 16384, kDeviceBuildMaxMeshes = 1024;
 constexpr size_t kDeviceTlasMin = 1u << 20;  // an LBVH over instances traverses markedly worse than the SAH tree (Menger sponge: +37 % k_extend), so
                                              // the TLAS goes to the GPU only where the host build would take seconds
 
+// Everything mrt_scene_upload checks before it touches the device: 0, or the MRT_E_* code with `why` set. Needs no context and no
+// GPU (mrt_scene_validate exposes it). blas_depth / tlas_depth: depth of the caller's trees in inner nodes (keep-topology uploads).
+static int validate_scene(const mrt_scene_desc* s, std::string& why, int& blas_depth, int& tlas_depth) {
+    blas_depth = tlas_depth = 0;
+    if (!s) { why = "scene is NULL"; return MRT_E_INVALID; }
+    if (s->abi_version != MRT_ABI_VERSION) { why = "mrt_scene_desc.abi_version mismatch"; return MRT_E_INVALID; }
+    if ((s->n_roots && !s->roots) || (s->n_nodes && !s->nodes) || (s->n_spheres && !s->spheres) || (s->n_tris && (!s->tri_verts || !s->tri_shading)) ||
+        (s->n_blas && !s->blas) || (s->n_instances && !s->instances) || (s->n_volumes && !s->volumes) || (s->n_materials && !s->materials) ||
+        (s->n_surfaces && !s->surfaces) || (s->n_textures && !s->textures) || (s->n_texels && !s->texels)) {
+        why = "an array of the scene is NULL while its count is not 0";
+        return MRT_E_INVALID;
+    }
+    if (s->background.kind < MRT_BG_SOLID || s->background.kind > MRT_BG_CUBEMAP) { why = "unknown background kind"; return MRT_E_INVALID; }
+    if (s->n_nodes >= (1ull << 29) || s->n_tris >= (1ull << 29) || s->n_spheres >= (1ull << 29) || s->n_instances >= (1ull << 29))
+        { why = "array too large for 29-bit primitive references"; return MRT_E_INVALID; }
+    for (uint32_t i = 0; i < s->n_roots; ++i) {
+        if (!ref_ok(s, s->roots[i], true)) { why = "root reference out of range"; return MRT_E_INVALID; }
+        if (MRT_REF_KIND(s->roots[i]) == MRT_PRIM_TRIANGLE) { why = "bare Triangle in the world list is not supported (wrap it in a Model)"; return MRT_E_UNSUPPORTED; }
+    }
+    auto mat_ok = [&](int32_t m, bool none_ok) { return (none_ok && m == -1) || (m >= 0 && (uint64_t)m < s->n_materials); };
+    auto surf_ok = [&](int32_t v) { return v >= 0 && (uint64_t)v < s->n_surfaces; };
+    for (uint64_t i = 0; i < s->n_surfaces; ++i) {
+        const mrt_surface& u = s->surfaces[i];
+        bool ok = true;
+        if (u.kind == MRT_SURF_TEXTURE) ok = u.a >= 0 && (uint64_t)u.a < s->n_textures;
+        else if (u.kind == MRT_SURF_YCBCR) ok = u.a >= 0 && (uint64_t)u.a < s->n_textures && u.b >= 0 && (uint64_t)u.b < s->n_textures;
+        else if (u.kind == MRT_SURF_BLEND) ok = surf_ok(u.a) && surf_ok(u.b) && (uint64_t)u.a < i && (uint64_t)u.b < i && u.mode >= 0 && u.mode <= 3;
+        else if (u.kind == MRT_SURF_FALLBACK) ok = surf_ok(u.a) && (uint64_t)u.a < i;
+        else if (u.kind != MRT_SURF_SOLID) ok = false;
+        if (!ok) { why = "malformed surface table entry " + std::to_string(i); return MRT_E_INVALID; }
+    }
+    for (uint64_t i = 0; i < s->n_textures; ++i) {
+        const mrt_texture& t = s->textures[i];
+        if (t.width == 0 || t.height == 0 || t.texel_offset + (uint64_t)t.width * t.height > s->n_texels) { why = "texture outside the texel array"; return MRT_E_INVALID; }
+        if (t.wrap != MRT_WRAP_REPEAT && t.wrap != MRT_WRAP_CLAMP) { why = "Mirror wrapping is not implemented (texture.rs:280)"; return MRT_E_UNSUPPORTED; }
+    }
+    for (uint64_t i = 0; i < s->n_materials; ++i) {
+        const mrt_material& m = s->materials[i];
+        bool ok = m.kind >= 0 && m.kind < MRT_MAT_KINDS;
+        if (ok && (m.kind == MRT_MAT_LAMBERTIAN || m.kind == MRT_MAT_METAL || m.kind == MRT_MAT_SPECULAR)) ok = surf_ok(m.surface);
+        if (ok && m.kind == MRT_MAT_MIX) ok = mat_ok(m.left, false) && mat_ok(m.right, false) && (uint64_t)m.left < i && (uint64_t)m.right < i;
+        if (ok && m.kind == MRT_MAT_EVE) {
+            int32_t pal;
+            std::memcpy(&pal, &m.p[0], 4);
+            ok = surf_ok(m.surface) && surf_ok(m.left) && surf_ok(m.right) && pal >= 0 && (uint64_t)pal + 4 <= s->n_surfaces;
+            for (int k = 0; ok && k < 4; ++k) ok = s->surfaces[pal + k].kind == MRT_SURF_SOLID;
+        }
+        if (!ok) { why = "malformed material table entry " + std::to_string(i); return MRT_E_INVALID; }
+    }
+    for (uint64_t i = 0; i < s->n_spheres; ++i)
+        if (!mat_ok(s->spheres[i].material, false)) { why = "sphere material out of range"; return MRT_E_INVALID; }
+    {
+        std::atomic<bool> bad{false};
+        parallel_for((size_t)s->n_tris, [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; ++i)
+                if (!mat_ok(s->tri_shading[i].material, false)) bad = true;
+        });
+        if (bad) { why = "triangle material out of range"; return MRT_E_INVALID; }
+    }
+    for (uint64_t i = 0; i < s->n_volumes; ++i) {
+        const mrt_volume& v = s->volumes[i];
+        if (!ref_ok(s, v.target, false)) { why = "volume target out of range"; return MRT_E_INVALID; }
+        if (MRT_REF_KIND(v.target) != MRT_PRIM_SPHERE && MRT_REF_KIND(v.target) != MRT_PRIM_INSTANCE)
+            { why = "Volume targets: Sphere, Model and Instance (geom.rs:595 is generic over Intersect)"; return MRT_E_UNSUPPORTED; }
+        if (!mat_ok(v.material, false)) { why = "volume material out of range"; return MRT_E_INVALID; }
+    }
+    if (s->background.kind == MRT_BG_SKYSPHERE && !surf_ok(s->background.surface[0])) { why = "background surface out of range"; return MRT_E_INVALID; }
+    if (s->background.kind == MRT_BG_CUBEMAP)
+        for (int k = 0; k < 6; ++k)
+            if (!surf_ok(s->background.surface[k])) { why = "background surface out of range"; return MRT_E_INVALID; }
+    blas_depth = 0;
+    const bool keep = (s->flags & MRT_SCENE_KEEP_TOPOLOGY) != 0;
+    for (uint64_t i = 0; i < s->n_blas; ++i) {
+        const mrt_blas& b = s->blas[i];
+        if ((uint64_t)b.first_tri + b.n_tris > s->n_tris) { why = "malformed BLAS table entry"; return MRT_E_INVALID; }
+        if (b.n_tris == 0) { why = "BLAS without triangles (BvhNode::new does not terminate on an empty list, geom.rs:130-144)"; return MRT_E_INVALID; }
+        if (b.root == MRT_REF_NONE) {  // a mesh without a caller tree (mrth_defer_mesh_bvh)
+            if (keep) { why = "MRT_SCENE_KEEP_TOPOLOGY needs the nodes of every BLAS"; return MRT_E_INVALID; }
+            continue;
+        }
+        if (MRT_REF_KIND(b.root) != MRT_PRIM_NODE || MRT_REF_INDEX(b.root) >= s->n_nodes) { why = "malformed BLAS table entry"; return MRT_E_INVALID; }
+        if (!keep) continue;  // the rebuild reads the BLAS's triangle range only, never the caller's nodes
+        int d = subtree_depth(s, b.root, false, why);
+        if (d < 0) return MRT_E_INVALID;
+        blas_depth = std::max(blas_depth, d);
+    }
+    for (uint64_t i = 0; i < s->n_instances; ++i) {
+        if (s->instances[i].blas >= s->n_blas) { why = "instance BLAS out of range"; return MRT_E_INVALID; }
+        if (!mat_ok(s->instances[i].material, true)) { why = "instance material out of range"; return MRT_E_INVALID; }
+    }
+    tlas_depth = 0;
+    for (uint32_t i = 0; i < s->n_roots; ++i) {
+        int d = subtree_depth(s, s->roots[i], true, why);
+        if (d == -2) return MRT_E_UNSUPPORTED;
+        if (d < 0) return MRT_E_INVALID;
+        tlas_depth = std::max(tlas_depth, d);
+    }
+    if (keep) {  // every node is converted below, reachable from a root or not: all of them must name children that exist
+        for (uint64_t i = 0; i < s->n_nodes; ++i) {
+            const mrt_node& n = s->nodes[i];
+            if (n.left == MRT_REF_NONE || !ref_ok(s, n.left, true) || (n.right != MRT_REF_NONE && !ref_ok(s, n.right, true)))
+                { why = "node " + std::to_string(i) + ": child reference out of range"; return MRT_E_INVALID; }
+        }
+    }
+    if (keep && tlas_depth + blas_depth + 2 > kStackSize)
+        { why = "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack"; return MRT_E_UNSUPPORTED; }
+    if (s->n_tris > kTriIndexMask) { why = "more than 2^27 triangles"; return MRT_E_UNSUPPORTED; }
+    return MRT_OK;
+}
+
+int mrt_scene_validate(const mrt_scene_desc* scene, char* why_out, size_t why_bytes) {
+    std::string why;
+    int blas_depth, tlas_depth;
+    const int rc = validate_scene(scene, why, blas_depth, tlas_depth);
+    if (why_out && why_bytes) {
+        const size_t n = std::min(why.size(), why_bytes - 1);
+        std::memcpy(why_out, why.data(), n);
+        why_out[n] = 0;
+    }
+    return rc;
+}
+
 static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device);
 
 static int comm_scene_broadcast(mrt_context* ctx, int root_rc);
@@ -1030,8 +1152,6 @@ int mrt_scene_upload(mrt_context* ctx, const mrt_scene_desc* s) {
 }
 
 static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool allow_device) {
-    if (!s) return fail(ctx, MRT_E_INVALID, "scene is NULL");
-    if (s->abi_version != MRT_ABI_VERSION) return fail(ctx, MRT_E_INVALID, "mrt_scene_desc.abi_version mismatch");
     MRT_CUDA(cudaSetDevice(ctx->device));
     // phase timing of the upload on stderr when MRT_UPLOAD_TIMING is set (measurement aid)
     const bool timing = std::getenv("MRT_UPLOAD_TIMING") != nullptr;
@@ -1043,104 +1163,12 @@ static int scene_upload_impl(mrt_context* ctx, const mrt_scene_desc* s, bool all
         t_prev = now;
     };
     // ---- validate ------------------------------------------------------------------------------------------
-    if (s->n_nodes >= (1ull << 29) || s->n_tris >= (1ull << 29) || s->n_spheres >= (1ull << 29) || s->n_instances >= (1ull << 29))
-        return fail(ctx, MRT_E_INVALID, "array too large for 29-bit primitive references");
-    for (uint32_t i = 0; i < s->n_roots; ++i) {
-        if (!ref_ok(s, s->roots[i], true)) return fail(ctx, MRT_E_INVALID, "root reference out of range");
-        if (MRT_REF_KIND(s->roots[i]) == MRT_PRIM_TRIANGLE) return fail(ctx, MRT_E_UNSUPPORTED, "bare Triangle in the world list is not supported (wrap it in a Model)");
-    }
-    auto mat_ok = [&](int32_t m, bool none_ok) { return (none_ok && m == -1) || (m >= 0 && (uint64_t)m < s->n_materials); };
-    auto surf_ok = [&](int32_t v) { return v >= 0 && (uint64_t)v < s->n_surfaces; };
-    for (uint64_t i = 0; i < s->n_surfaces; ++i) {
-        const mrt_surface& u = s->surfaces[i];
-        bool ok = true;
-        if (u.kind == MRT_SURF_TEXTURE) ok = u.a >= 0 && (uint64_t)u.a < s->n_textures;
-        else if (u.kind == MRT_SURF_YCBCR) ok = u.a >= 0 && (uint64_t)u.a < s->n_textures && u.b >= 0 && (uint64_t)u.b < s->n_textures;
-        else if (u.kind == MRT_SURF_BLEND) ok = surf_ok(u.a) && surf_ok(u.b) && (uint64_t)u.a < i && (uint64_t)u.b < i && u.mode >= 0 && u.mode <= 3;
-        else if (u.kind == MRT_SURF_FALLBACK) ok = surf_ok(u.a) && (uint64_t)u.a < i;
-        else if (u.kind != MRT_SURF_SOLID) ok = false;
-        if (!ok) return fail(ctx, MRT_E_INVALID, "malformed surface table entry " + std::to_string(i));
-    }
-    for (uint64_t i = 0; i < s->n_textures; ++i) {
-        const mrt_texture& t = s->textures[i];
-        if (t.width == 0 || t.height == 0 || t.texel_offset + (uint64_t)t.width * t.height > s->n_texels) return fail(ctx, MRT_E_INVALID, "texture outside the texel array");
-        if (t.wrap != MRT_WRAP_REPEAT && t.wrap != MRT_WRAP_CLAMP) return fail(ctx, MRT_E_UNSUPPORTED, "Mirror wrapping is not implemented (texture.rs:280)");
-    }
-    for (uint64_t i = 0; i < s->n_materials; ++i) {
-        const mrt_material& m = s->materials[i];
-        bool ok = m.kind >= 0 && m.kind < MRT_MAT_KINDS;
-        if (ok && (m.kind == MRT_MAT_LAMBERTIAN || m.kind == MRT_MAT_METAL || m.kind == MRT_MAT_SPECULAR)) ok = surf_ok(m.surface);
-        if (ok && m.kind == MRT_MAT_MIX) ok = mat_ok(m.left, false) && mat_ok(m.right, false) && (uint64_t)m.left < i && (uint64_t)m.right < i;
-        if (ok && m.kind == MRT_MAT_EVE) {
-            int32_t pal;
-            std::memcpy(&pal, &m.p[0], 4);
-            ok = surf_ok(m.surface) && surf_ok(m.left) && surf_ok(m.right) && pal >= 0 && (uint64_t)pal + 4 <= s->n_surfaces;
-            for (int k = 0; ok && k < 4; ++k) ok = s->surfaces[pal + k].kind == MRT_SURF_SOLID;
-        }
-        if (!ok) return fail(ctx, MRT_E_INVALID, "malformed material table entry " + std::to_string(i));
-    }
-    for (uint64_t i = 0; i < s->n_spheres; ++i)
-        if (!mat_ok(s->spheres[i].material, false)) return fail(ctx, MRT_E_INVALID, "sphere material out of range");
-    {
-        std::atomic<bool> bad{false};
-        parallel_for((size_t)s->n_tris, [&](size_t a, size_t b) {
-            for (size_t i = a; i < b; ++i)
-                if (!mat_ok(s->tri_shading[i].material, false)) bad = true;
-        });
-        if (bad) return fail(ctx, MRT_E_INVALID, "triangle material out of range");
-    }
-    for (uint64_t i = 0; i < s->n_volumes; ++i) {
-        const mrt_volume& v = s->volumes[i];
-        if (!ref_ok(s, v.target, false)) return fail(ctx, MRT_E_INVALID, "volume target out of range");
-        if (MRT_REF_KIND(v.target) != MRT_PRIM_SPHERE && MRT_REF_KIND(v.target) != MRT_PRIM_INSTANCE)
-            return fail(ctx, MRT_E_UNSUPPORTED, "Volume targets: Sphere, Model and Instance (geom.rs:595 is generic over Intersect)");
-        if (!mat_ok(v.material, false)) return fail(ctx, MRT_E_INVALID, "volume material out of range");
-    }
-    if (s->background.kind == MRT_BG_SKYSPHERE && !surf_ok(s->background.surface[0])) return fail(ctx, MRT_E_INVALID, "background surface out of range");
-    if (s->background.kind == MRT_BG_CUBEMAP)
-        for (int k = 0; k < 6; ++k)
-            if (!surf_ok(s->background.surface[k])) return fail(ctx, MRT_E_INVALID, "background surface out of range");
     std::string why;
-    int blas_depth = 0;
+    int blas_depth = 0, tlas_depth = 0;
+    if (int vrc = validate_scene(s, why, blas_depth, tlas_depth)) return fail(ctx, vrc, why);
     const bool keep = (s->flags & MRT_SCENE_KEEP_TOPOLOGY) != 0;
-    for (uint64_t i = 0; i < s->n_blas; ++i) {
-        const mrt_blas& b = s->blas[i];
-        if ((uint64_t)b.first_tri + b.n_tris > s->n_tris) return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
-        if (b.n_tris == 0) return fail(ctx, MRT_E_INVALID, "BLAS without triangles (BvhNode::new does not terminate on an empty list, geom.rs:130-144)");
-        if (b.root == MRT_REF_NONE) {  // a mesh without a caller tree (mrth_defer_mesh_bvh)
-            if (keep) return fail(ctx, MRT_E_INVALID, "MRT_SCENE_KEEP_TOPOLOGY needs the nodes of every BLAS");
-            continue;
-        }
-        if (MRT_REF_KIND(b.root) != MRT_PRIM_NODE || MRT_REF_INDEX(b.root) >= s->n_nodes) return fail(ctx, MRT_E_INVALID, "malformed BLAS table entry");
-        if (!keep) continue;  // the rebuild reads the BLAS's triangle range only, never the caller's nodes
-        int d = subtree_depth(s, b.root, false, why);
-        if (d < 0) return fail(ctx, MRT_E_INVALID, why);
-        blas_depth = std::max(blas_depth, d);
-    }
-    for (uint64_t i = 0; i < s->n_instances; ++i) {
-        if (s->instances[i].blas >= s->n_blas) return fail(ctx, MRT_E_INVALID, "instance BLAS out of range");
-        if (!mat_ok(s->instances[i].material, true)) return fail(ctx, MRT_E_INVALID, "instance material out of range");
-    }
-    int tlas_depth = 0;
-    for (uint32_t i = 0; i < s->n_roots; ++i) {
-        int d = subtree_depth(s, s->roots[i], true, why);
-        if (d == -2) return fail(ctx, MRT_E_UNSUPPORTED, why);
-        if (d < 0) return fail(ctx, MRT_E_INVALID, why);
-        tlas_depth = std::max(tlas_depth, d);
-    }
-    if (keep) {  // every node is converted below, reachable from a root or not: all of them must name children that exist
-        for (uint64_t i = 0; i < s->n_nodes; ++i) {
-            const mrt_node& n = s->nodes[i];
-            if (n.left == MRT_REF_NONE || !ref_ok(s, n.left, true) || (n.right != MRT_REF_NONE && !ref_ok(s, n.right, true)))
-                return fail(ctx, MRT_E_INVALID, "node " + std::to_string(i) + ": child reference out of range");
-        }
-    }
-    if (keep && tlas_depth + blas_depth + 2 > kStackSize)
-        return fail(ctx, MRT_E_UNSUPPORTED, "BVH too deep for the " + std::to_string(kStackSize) + "-entry traversal stack");
-
     lap("validate");
     // ---- acceleration structure: the caller's topology re-laid out, or (default) a SAH rebuild -----------------------------
-    if (s->n_tris > kTriIndexMask) return fail(ctx, MRT_E_UNSUPPORTED, "more than 2^27 triangles");
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     DScene d{};
