@@ -1040,7 +1040,8 @@ static int validate_scene(const mrt_scene_desc* s, std::string& why, int& blas_d
     }
     for (uint64_t i = 0; i < s->n_textures; ++i) {
         const mrt_texture& t = s->textures[i];
-        if (t.width == 0 || t.height == 0 || t.texel_offset + (uint64_t)t.width * t.height > s->n_texels) { why = "texture outside the texel array"; return MRT_E_INVALID; }
+        if (t.width == 0 || t.height == 0 || t.texel_offset > s->n_texels || (uint64_t)t.width * t.height > s->n_texels - t.texel_offset)  // no wrap-around for huge offsets
+            { why = "texture outside the texel array"; return MRT_E_INVALID; }
         if (t.wrap != MRT_WRAP_REPEAT && t.wrap != MRT_WRAP_CLAMP) { why = "Mirror wrapping is not implemented (texture.rs:280)"; return MRT_E_UNSUPPORTED; }
     }
     for (uint64_t i = 0; i < s->n_materials; ++i) {

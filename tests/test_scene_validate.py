@@ -130,6 +130,8 @@ def test_every_rule_has_a_failing_case():
     expect(b2, tex_index, -1, "malformed surface table entry")
     def tex_range(e): e.t["textures"]["texel_offset"][0] = e.desc.n_texels
     expect(b2, tex_range, -1, "texture outside the texel array")
+    def tex_wrap_around(e): e.t["textures"]["texel_offset"][0] = (1 << 64) - 1  # offset + w * h wraps to a small number
+    expect(b2, tex_wrap_around, -1, "texture outside the texel array")
     def tex_zero(e): e.t["textures"]["width"][0] = 0
     expect(b2, tex_zero, -1, "texture outside the texel array")
     def tex_mirror(e): e.t["textures"]["wrap"][0] = 0
